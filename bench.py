@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the pseudo-label mining step (BASELINE.json metric: Mpixel/s + fraction of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one target batch + one source batch
+(tools/train_ssl_uem.py:209-216 + the detached part of loss_calc_uvem, balance.py:372-396):
+    label_refine(mode='all', temp=2) -> pseudo_selection(0.8, 0.6) -> update_prototype(feat_s, label_s)
+    -> entropy + UVEM weight of the refined soft labels.
+Default workload = BASELINE.json configs[1]: ISPRS 8x6x512x512, 2048-ch features at 1/16 res.
+
+One JSON line is printed by rank 0 (contract in the task statement):
+  value     whole-job Mpixel/s, inputs resident in HBM, K steps replayed as CUDA graphs, CUDA-event timed,
+            max over ranks; inputs rotate over several buffer sets so that every step reads cold data
+  e2e       same metric through the public drop-in API with HOST (pinned) inputs: H2D of every input and D2H
+            of the hard labels inside the timed region
+  roofline  fused refine kernel: algorithmic bytes / CUDA-event duration vs the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (a torch-CPU restatement of the reference, pinned to it by tests/golden)
+            on this box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+UVEM = (0.2, 0.7, 4.0)      # --uvem-m/-t/-g, tools/train_ssl_uem.py:59-61
+CUTOFF = (0.8, 0.6)         # CUTOFF_TOP/LOW, configs/st/uemda/2potsdam.py:24-25
+DECAY = 0.996               # tools/train_ssl_uem.py:117
+TEMP = 2.0                  # --refine-temp
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="cfg2_isprs_8x6x512")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=3, help="rotating input buffer sets (working set > L2)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=4)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = []
+        with open(self.tmp.name) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    rows.append(parts)
+        os.unlink(self.tmp.name)
+        sm = []
+        reasons = set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_fn(wl, n_images):
+    from oracle import uem_oracle as O
+    from uemda_b200.synth import make_inputs
+    inp = make_inputs(wl, seed=2333, b=n_images)
+    protos = inp["prototypes"]
+
+    def step():
+        return O.mining_step(inp, protos, wl.c, mode="all", temp=TEMP, cutoff_top=CUTOFF[0], cutoff_low=CUTOFF[1],
+                             decay=DECAY, uvem=UVEM, scale_factor=wl.scale)
+    return step, n_images * wl.H * wl.W
+
+
+def run_cpu_baseline(wl, n_images, warmup=1, steps=3):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, px = cpu_step_fn(wl, n_images)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return {"value": px / t / 1e6, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d of %d images of %s, %d warm-up + median of %d steps (%.3f s/step), torch CPU oracle "
+                      "(oracle/uem_oracle.py)" % (n_images, wl.b, wl.name, warmup, steps, t)}
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's CPU implementation of the path, i.e. the oracle port (the reference is
+    pure Python/torch and cannot travel to the GPU box; the port is pinned to it by tests/golden)."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_img = min(wl.b, args.cpu_sample_images)
+    step, px = cpu_step_fn(wl, n_img)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = px / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "pseudo-label mining throughput", "value": val, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "b": wl.b, "c": wl.c, "H": wl.H, "W": wl.W, "k": wl.k, "feat_scale": wl.scale,
+                   "regions": wl.regions},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d of %d images per step" % (n_img, wl.b)},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+class _Log:
+    def info(self, *a, **k):
+        pass
+
+
+def make_sets(wl, nsets, dev, rank):
+    """nsets distinct device copies of one seeded batch (batch-rolled so contents differ); pinned host copy of set 0."""
+    from uemda_b200.synth import make_inputs
+    inp = make_inputs(wl, seed=2333 + rank)
+    keys = ("soft", "sup", "feat", "pred1", "pred2", "label_s", "feat_s")
+    host = {k: inp[k].pin_memory() for k in keys}
+    sets = []
+    for i in range(nsets):
+        sets.append({k: torch.roll(host[k], shifts=i, dims=0).to(dev) for k in keys})
+    return inp, host, sets
+
+
+def main():
+    args = parse()
+    from uemda_b200.synth import WORKLOADS
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from uemda_b200 import _lib, config, mining, ops
+    from uemda_b200.gast.alignment import Aligner, DownscaleLabel
+    from uemda_b200.gast.pseudo_generation import pseudo_selection
+    lib = _lib.load()
+
+    inp, host, sets = make_sets(wl, args.sets, dev, rank)
+    R = int(inp["ignore_id"]) + 1
+    al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c, ignore_label=-1, decay=DECAY)
+    al.downscale_gt = DownscaleLabel(wl.scale, wl.c, -1, 0.75)
+    al.prototypes = inp["prototypes"].to(dev)
+    al.num_regions = R
+    miner = mining.ShardedMiner(al) if world > 1 else None
+    ws = None
+
+    def step_resident(s):
+        """device-resident step, no host sync (strict asserts off)"""
+        nonlocal ws
+        ignored = miner.global_ignored_id(s["sup"]) if miner else None
+        refined, hard = mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=al.prototypes, pred1=s["pred1"],
+                                             pred2=s["pred2"], sup=s["sup"], num_regions=R, ignored_id=ignored, eps=al.eps,
+                                             select=(CUTOFF[0], CUTOFF[1], -1), ws=ws)
+        if miner:
+            miner.update_prototype(s["feat_s"], s["label_s"])
+        else:
+            al.update_prototype(s["feat_s"], s["label_s"])
+        ent, wgt = ops.entropy_uvem_weight(refined, *UVEM)
+        return refined, hard, ent, wgt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    config.strict_asserts = False
+    need = lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, R)
+    ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+
+    # ---- warm-up (eager), then graph capture: one graph per buffer set
+    for i in range(max(args.warmup, 3)):
+        step_resident(sets[i % args.sets])
+    barrier()
+    graphs = None
+    if not args.no_graph:
+        try:
+            graphs = []
+            keep = []
+            for s in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    keep.append(step_resident(s))
+                graphs.append(g)
+            for g in graphs:
+                g.replay()
+            barrier()
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print("graph capture failed, timing eagerly: %r" % (e,), file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % args.sets].replay()
+        else:
+            step_resident(sets[i % args.sets])
+
+    for i in range(args.warmup):
+        run_step(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launches0 = lib.uem_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches_eager_per_step = None
+    if graphs is None:
+        launches_eager_per_step = (lib.uem_kernel_launches() - launches0) / args.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- kernel-level timing (eager, event pair recorded inside the C call around the fused refine kernel)
+    kern_ms = []
+    n_k = min(args.steps, 50)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
+    for a, b2 in evs:  # torch creates the cudaEvent_t lazily on the first record()
+        a.record()
+        b2.record()
+    torch.cuda.synchronize()
+    l0 = lib.uem_kernel_launches()
+    for i in range(n_k):
+        lib.uem_profile_refine_events(evs[i][0].cuda_event, evs[i][1].cuda_event)
+        step_resident(sets[i % args.sets])
+    torch.cuda.synchronize()
+    per_step_launches = (lib.uem_kernel_launches() - l0) / max(n_k, 1)
+    for a, b2 in evs:
+        try:
+            kern_ms.append(a.elapsed_time(b2))
+        except Exception:  # noqa: BLE001
+            pass
+    refine_ms = statistics.mean(kern_ms) if kern_ms else None
+
+    # ---- e2e: public drop-in API, host (pinned) inputs, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        config.strict_asserts = True
+        al.num_regions = None  # the un-hinted public path: reads sup.max() back like torch_scatter does
+        hard_host = torch.empty((wl.b, wl.H, wl.W), dtype=torch.int64).pin_memory()
+        h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+        d2h = hard_host.numel() * hard_host.element_size()
+
+        def step_e2e():
+            d = {k: host[k].to(dev, non_blocking=True) for k in host}
+            refined = al.label_refine(d["sup"], d["feat"], [d["pred1"], d["pred2"]], d["soft"], refine=True, mode="all", temp=TEMP)
+            hard = pseudo_selection(refined, CUTOFF[0], CUTOFF[1], "tensor", -1)
+            if miner:
+                miner.update_prototype(d["feat_s"], d["label_s"])
+            else:
+                al.update_prototype(d["feat_s"], d["label_s"])
+            ops.entropy_uvem_weight(refined, *UVEM)
+            hard_host.copy_(hard, non_blocking=True)
+
+        n_e = max(3, min(args.steps, 30))
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_e):
+            step_e2e()
+        b2.record()
+        barrier()
+        e_ms = a.elapsed_time(b2) / n_e
+        te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item())
+        e2e = {"value": world * wl.pixels / e_ms / 1e3, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "steps": n_e,
+               "api": "Aligner.label_refine + pseudo_selection + Aligner.update_prototype + entropy/UVEM weight"}
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        alg_bytes = wl.pixels * (4 * wl.c + 8 + 4 * wl.c)  # refine kernel: read soft + sup, write refined
+        roof = {"bound": "hbm", "kernel": "refine_kernel (fused label_refine, all views)", "achieved": None, "peak": peak,
+                "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                "kernel_ms": refine_ms}
+        if refine_ms:
+            roof["achieved"] = alg_bytes / (refine_ms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+        tpath = os.path.join(ROOT, "profiles", "refine_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                roof["traffic"] = json.load(open(tpath)).get(wl.name)
+            except Exception:  # noqa: BLE001
+                pass
+        chain_bytes = wl.pixels * (4 * wl.c + 8 + 4 * wl.c + 8) + wl.b * wl.k * wl.h * wl.w * 4 \
+            + wl.pixels * 8 + wl.b * wl.k * wl.h * wl.w * 4 + wl.pixels * (4 * wl.c + 8)
+        line = {
+            "metric": "pseudo-label mining throughput", "value": world * wl.pixels / ms / 1e3, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "b_per_gpu": wl.b, "c": wl.c, "H": wl.H, "W": wl.W, "k": wl.k, "feat_scale": wl.scale,
+                       "regions": wl.regions, "step": "label_refine(all)+pseudo_selection+update_prototype+entropy/uvem_weight",
+                       "l2_policy": "inputs rotate over %d buffer sets (%.0f MiB each) so each step reads cold data" % (
+                           args.sets, sum(v.numel() * v.element_size() for v in sets[0].values()) / 2 ** 20),
+                       "cuda_graph": graphs is not None, "parallelism": "batch-sharded x%d" % world},
+            "step_algorithmic_bytes": chain_bytes,
+            "step_hbm_frac": chain_bytes / (ms * 1e-3) / 1e9 / peak,
+            "roofline": roof,
+            "gpu_launches": int(round(per_step_launches * args.steps)),
+            "kernels_per_step": per_step_launches,
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = run_cpu_baseline(wl, min(wl.b, args.cpu_sample_images))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+/*
+ * uem_b200.h -- C-ABI of libuem_b200.so: hand-written sm_100a kernels for UemDA's
+ * uncertain-example pseudo-label mining path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - maps are contiguous NCHW (class/feature planes of H*W pixels, pixel stride 1);
+ *   - labels, pseudo-labels and superpixel ids are int64 (the reference's dtypes,
+ *     uemda/datasets/basedata.py:77-79,87), probabilities/logits/features are fp32;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success; on failure it returns non-zero and
+ *     uem_last_error() describes why (thread-local, valid until the next call);
+ *   - no function allocates device memory, synchronises the device or copies to the host:
+ *     workspaces are caller-provided (sizes via the *_ws_bytes helpers);
+ *   - class count c is limited to UEM_MAX_CLASSES (ISPRS = 6, LoveDA = 7).
+ *
+ * Each entry point cites the reference interface it replaces (file:line in StuLiu/UemDA).
+ */
+#ifndef UEM_B200_H
+#define UEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define UEM_API __attribute__((visibility("default")))
+#else
+#define UEM_API
+#endif
+
+#define UEM_MAX_CLASSES 8
+#define UEM_ABI_VERSION 1
+
+/* label_refine view bits (alignment.py:215 'p', :225 'l', :238 's'; 'all' = all three) */
+#define UEM_VIEW_PROTO 1
+#define UEM_VIEW_PRED 2
+#define UEM_VIEW_SUP 4
+
+/* region reduce ops (torch_scatter.scatter reduce=..., alignment.py:187,245) */
+#define UEM_REDUCE_SUM 0
+#define UEM_REDUCE_MAX 1
+#define UEM_REDUCE_MEAN 2
+
+UEM_API const char* uem_last_error(void);
+UEM_API int uem_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+UEM_API int64_t uem_kernel_launches(void);
+/* measurement hook: the next uem_label_refine_f32 / uem_mine_refine_select_f32 call on this thread records
+ * the two cudaEvent_t (passed as void*) immediately before / after its fused refine kernel */
+UEM_API int uem_profile_refine_events(void* start_event, void* stop_event);
+/* binds the calling thread to a CUDA device (the library links cudart statically) */
+UEM_API int uem_set_device(int device);
+
+/* ---- a1-a4: fused logits pass -------------------------------------------------------
+ * soft = mean_heads softmax(bilinear_up(x_head, align_corners=True) / temp)  [train_align_uem.py:158-160,
+ * Encoder.py:153-155, alignment.py:311-314]; conf/argmax = max / first-index argmax over classes
+ * [pseudo_generation.py:47,148]; entropy = sum_c -p log p [balance.py:372].
+ * x1,x2: (b,c,h,w) (x2 may be NULL); outputs (any may be NULL): soft (b,c,H,W), conf (b,H,W),
+ * entropy (b,H,W), argmax (b,H,W) int64. */
+UEM_API int uem_softmax_conf_entropy_argmax_f32(const float* x1, const float* x2, int b, int c, int h, int w,
+                                        int H, int W, float temp, float* soft, float* conf,
+                                        float* entropy, int64_t* argmax, void* stream);
+
+/* ---- a2+a3: entropy of a probability map + UVEM weight ---------------------------------
+ * balance.py:368-373,396-423.  soft (b,c,HW) -> entropy (b*HW), weight (b*HW) (either may be NULL).
+ * coef_left/right are the reference's Python-double coefficients -1/m^2 and -1/(t-m)^2 rounded to
+ * fp32 by the caller; inv_gamma = fp32(1/gamma). */
+UEM_API int uem_entropy_uvem_weight_f32(const float* soft, int b, int c, int64_t hw, float m, float t,
+                                float inv_gamma, float coef_left, float coef_right,
+                                float* entropy, float* weight, void* stream);
+/* UVEMLoss.get_weight on an arbitrary uncertainty vector, balance.py:396-423 */
+UEM_API int uem_uvem_weight_f32(const float* u, int64_t n, float m, float t, float inv_gamma,
+                        float coef_left, float coef_right, float* weight, void* stream);
+/* detached per-pixel factors of UVEMLoss/UPSLoss.forward, balance.py:372-382 (uvem) / :331-342 (ups):
+ * entropy u of soft, gate = (u > t) as uint8, weight = get_weight(u) (1.0 if use_weight==0),
+ * valid_cnt[0] += #( u <= t && target != ignore ).  target int64 (b*HW). valid_cnt must be zeroed. */
+UEM_API int uem_uvem_terms_f32(const float* soft, const int64_t* target, int b, int c, int64_t hw, float m,
+                       float t, float inv_gamma, float coef_left, float coef_right, int use_weight,
+                       int64_t ignore_label, float* weight, uint8_t* gate, int64_t* valid_cnt,
+                       void* stream);
+
+/* ---- a5: class-wise thresholded pseudo labels ------------------------------------------
+ * pseudo_generation.py:59-93 (variant 0) and :24-56 (variant 1).
+ * uem_class_max_f32: per-(b,c) max / min over HW pixels of mask (b,c,HW) -> cmax,cmin (b*c);
+ *   has_nan[0] set non-zero if any NaN was seen.  ws: uem_class_max_ws_bytes(b,c,hw) bytes. */
+UEM_API int64_t uem_class_max_ws_bytes(int b, int c, int64_t hw);
+UEM_API int uem_class_max_f32(const float* mask, int b, int c, int64_t hw, float* cmax, float* cmin,
+                      int32_t* has_nan, void* ws, void* stream);
+/* thr[b,c] = fmaxf(cmax*cutoff_top, cutoff_low) in fp32; strict '>' ; kept iff exactly one class wins */
+UEM_API int uem_pseudo_select_f32(const float* mask, const float* cmax, int b, int c, int64_t hw,
+                          float cutoff_top, float cutoff_low, int64_t ignore_label, int variant,
+                          int64_t* out, void* stream);
+
+/* ---- a6s/a7 seam: torch_scatter.scatter over superpixel ids -----------------------------
+ * alignment.py:187 (sum, int64) and :245 (max, f32).  src element (bi,n,ci) lives at
+ * src[bi*src_sb + n*src_sn + ci*src_sc] (element strides: (b,N,c) contiguous = {N*c,c,1};
+ * an NCHW map viewed as (b,N,c) = {c*N,1,N}).  index (b,N) int64 in [0,R).  out (b,R,c) dense,
+ * untouched slots 0.  ws: uem_region_reduce_ws_bytes(b,R,c). */
+UEM_API int uem_i64_minmax(const int64_t* x, int64_t n, int64_t* out_min_max /*[2]*/, void* stream);
+UEM_API int64_t uem_region_reduce_ws_bytes(int b, int64_t R, int c);
+UEM_API int uem_region_reduce_f32(const float* src, int64_t src_sb, int64_t src_sn, int64_t src_sc,
+                          const int64_t* index, int b, int64_t N, int c, int64_t R, int op,
+                          float* out, void* ws, void* stream);
+UEM_API int uem_region_reduce_i64(const int64_t* src, int64_t src_sb, int64_t src_sn, int64_t src_sc,
+                          const int64_t* index, int b, int64_t N, int c, int64_t R, int op,
+                          int64_t* out, void* ws, void* stream);
+
+/* ---- a7: Aligner.superpixel_expand, alignment.py:175-192 -------------------------------
+ * hard (b,N) int64 in [-1,c) (ignore_label dropped), sup (b,N) int64 in [0,R) -> out (b,N) int64:
+ * majority class of the pixel's region (first index on ties), -1 if the region has no labelled pixel.
+ * ws: uem_superpixel_expand_ws_bytes(b,R,c). */
+UEM_API int64_t uem_superpixel_expand_ws_bytes(int b, int64_t R, int c);
+UEM_API int uem_superpixel_expand_i64(const int64_t* hard, const int64_t* sup, int b, int64_t N, int c,
+                              int64_t R, int64_t ignore_label, int64_t* out, void* ws, void* stream);
+
+/* ---- a8: DownscaleLabel.forward, alignment.py:484-509 ----------------------------------
+ * label (b,H,W) int64 -> out (b,H/s,W/s) int64.  status[0] |= 1 if a label outside
+ * {ignore} U [0,n_classes) was seen (the reference's one_hot raises). */
+UEM_API int uem_downscale_label_i64(const int64_t* label, int b, int H, int W, int scale, int n_classes,
+                            int64_t ignore_label, float min_ratio, int64_t* out, int32_t* status,
+                            void* stream);
+
+/* ---- a9: Aligner._pearson_dist, alignment.py:424-451 -----------------------------------
+ * nchw: feat (b,k,hw) planar, protos (m,k) row-major -> out (b,m,hw) planar:
+ *   out = dist, or 1/dist if reciprocal!=0 (alignment.py:216).  m <= UEM_MAX_CLASSES.
+ * rows: feat1 (n,k), feat2 (m,k) row-major -> out (n,m) row-major, any m.
+ * ws: uem_pearson_ws_bytes(m,k). */
+UEM_API int64_t uem_pearson_ws_bytes(int m, int k);
+UEM_API int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_t hw, const float* protos, int m,
+                              float eps, int reciprocal, float* out, void* ws, void* stream);
+UEM_API int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, const float* feat2, int m,
+                              float eps, float* out, void* ws, void* stream);
+
+/* ---- a6: Aligner.label_refine, alignment.py:194-293 ------------------------------------
+ * views: bitmask of UEM_VIEW_*.  simi (b,c,h,w): 1/pearson distance at feature resolution (PROTO view);
+ * pred1/pred2 (b,c,h,w) logits (pred2 may be NULL) (PRED view); sup (b,H,W) int64 + region_max
+ * (b,R,c) from uem_region_reduce_f32(MAX) + ignored_id (device pointer to the batch-global max id,
+ * alignment.py:241) (SUP view).  soft (b,c,H,W) -> out (b,c,H,W).
+ * class_max_partial (optional, may be NULL): per-CTA maxima of `out`, layout
+ * (b, uem_label_refine_partials(H), c+1) = [c per-class maxima | overall minimum] (NaN-poisoned if the
+ * CTA produced a NaN), consumed by uem_pseudo_select_partials_f32. */
+UEM_API int uem_label_refine_partials(int H);
+UEM_API int uem_label_refine_f32(int views, const float* simi, const float* pred1, const float* pred2, int h,
+                         int w, const int64_t* sup, const float* region_max, int64_t R,
+                         const int64_t* ignored_id, const float* soft, int b, int c, int H, int W,
+                         float temp, float* out, float* class_max_partial, void* stream);
+/* a5 fed by the partial maxima written by uem_label_refine_f32 (no second pass for the class max) */
+UEM_API int uem_pseudo_select_partials_f32(const float* mask, const float* class_max_partial, int n_partials,
+                                   int b, int c, int64_t hw, float cutoff_top, float cutoff_low,
+                                   int64_t ignore_label, int64_t* out, void* stream);
+
+/* ---- fused chain: label_refine -> pseudo_selection in one call, no host sync -----------------
+ * tools/train_ssl_uem.py:209-214 (vis_corrected_pseudo_labels.py:185-189).  feat (b,k,h,w), protos (c,k),
+ * pred1/pred2 (b,c,h,w), sup (b,H,W) with ids in [0,R) (R = capacity of the region table, >= max id+1),
+ * ignored_id: device pointer to the batch-global max id or NULL (then computed from sup, alignment.py:241),
+ * soft (b,c,H,W) -> refined (b,c,H,W), hard (b,H,W) int64 (NULL = skip the selection).
+ * ws: uem_mine_ws_bytes(...) bytes; ws[0..3] int32 status word: bit 2 = superpixel id outside [0,R). */
+UEM_API int64_t uem_mine_ws_bytes(int b, int c, int H, int W, int h, int w, int k, int64_t R);
+UEM_API int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos,
+                               const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
+                               int64_t R, const int64_t* ignored_id, const float* soft, int b, int c, int H,
+                               int W, float temp, float eps, float cutoff_top, float cutoff_low,
+                               int64_t ignore_label, float* refined, int64_t* hard, void* ws, void* stream);
+
+/* ---- a13: Aligner.get_prototype_weight_4pixel, alignment.py:295-309 --------------------- */
+UEM_API int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, const int64_t* hard, int b, int c,
+                                int H, int W, int64_t ignore_label, float eps, float* out, void* stream);
+
+/* ---- a10-a12: prototypes ----------------------------------------------------------------
+ * accumulate: feat (b,k,hw) planar, label (b,hw) int64 in {ignore} U [0,c) ->
+ *   sums (c,k) fp32 and counts (c) int64 (OVERWRITTEN, deterministic order).  alignment.py:341-348,109-119.
+ * accumulate_soft: soft (b,c,H,W) bilinearly down-sampled (align_corners) to (h,w) as weights ->
+ *   sums (c,k) (alignment.py:98-104, before the /n mean).
+ * finalize: local = sums/(cnt+eps), classes with cnt<1 keep proto_old (counts==NULL: local = sums/mean_n,
+ *   the torch.mean of alignment.py:104); proto_new = (1-decay)*local +
+ *   decay*proto_old with one_minus_decay/decay pre-rounded to fp32 by the caller (alignment.py:347-353,463-466).
+ * ws: uem_proto_accum_ws_bytes(b,c,k). */
+UEM_API int64_t uem_proto_accum_ws_bytes(int b, int c, int k);
+UEM_API int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t hw, const int64_t* label, int c,
+                             int64_t ignore_label, float* sums, int64_t* counts, void* ws, void* stream);
+UEM_API int64_t uem_proto_accum_soft_ws_bytes(int b, int c, int k, int h, int w);
+UEM_API int uem_proto_accum_soft_f32(const float* feat, int b, int k, int h, int w, const float* soft, int c,
+                             int H, int W, float* sums, void* ws, void* stream);
+UEM_API int uem_proto_finalize_ema_f32(const float* sums, const int64_t* counts, int64_t mean_n,
+                               const float* proto_old, int c, int k, float eps, float one_minus_decay,
+                               float decay, float* local_out, float* proto_new, void* stream);
+
+/* ---- a14/a15: histograms ------------------------------------------------------------------
+ * class_hist: hist[0..c) = #label==ci, hist[c] = #label!=ignore (balance.py:45-52); hist must be zeroed.
+ * class_weight_lookup: out[i] = table[label[i]] or 0 for ignore (balance.py:29-32).
+ * hist_f32: torch.histc semantics (balance.py:193): bins over [lo,hi], x==hi in last bin, outside dropped;
+ *   hist must be zeroed. */
+UEM_API int uem_class_hist_i64(const int64_t* label, int64_t n, int c, int64_t ignore_label, int64_t* hist,
+                       void* stream);
+UEM_API int uem_class_weight_lookup_f32(const int64_t* label, int64_t n, int c, int64_t ignore_label,
+                                const float* table, float* out, void* stream);
+UEM_API int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float hi, int64_t* hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UEM_B200_H */

@@ -1,0 +1,294 @@
+// a8: DownscaleLabel; a10-a12: masked class-prototype accumulation, soft-weighted accumulation, EMA.
+// Reference: uemda/gast/alignment.py:484-509 (DownscaleLabel.forward), :328-355
+// (_compute_local_prototypes), :107-126 (update_avg/init_avg), :92-105 (update_prototype_bytarget),
+// :463-466 (_ema), :468-481 (_index2onehot).
+//
+// The reference builds one-hot tensors ((b,c+1,H,W) f32, (n,c) int64) and an (n,c,k) broadcast product
+// (403 MB at config 2).  Here: DownscaleLabel is one pass over the int64 label map with per-thread
+// register bins; the prototype sums read the NCHW feature map exactly once (one warp per (image,
+// channel) row, 128-bit loads, class ids staged as bytes in shared memory, c register accumulators)
+// and are combined over the batch in a fixed order, so results are bit-reproducible run to run.
+#include "uem_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------- DownscaleLabel
+// one CTA per (output row, image): s input rows x W columns
+template <int C>
+__global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
+                                                        int64_t ignore_label, float min_ratio, int vec,
+                                                        int64_t* __restrict__ out, int32_t* __restrict__ status) {
+    extern __shared__ unsigned bins[];  // [w][C+1]
+    const int oy = blockIdx.x, bi = blockIdx.y;
+    for (int i = threadIdx.x; i < w * (C + 1); i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    const int64_t* base = label + ((int64_t)bi * H + (int64_t)oy * s) * W;
+    const int usedW = w * s;  // trailing columns that do not fill a block are dropped (alignment.py:500)
+    const int step = vec ? 2 : 1;
+    int bad = 0;
+    for (int x0 = threadIdx.x * step; x0 < usedW; x0 += blockDim.x * step) {
+        unsigned cnt0[C + 1], cnt1[C + 1];
+#pragma unroll
+        for (int ci = 0; ci <= C; ++ci) { cnt0[ci] = 0; cnt1[ci] = 0; }
+        const bool two = vec && (x0 + 1 < usedW);
+#pragma unroll 4
+        for (int r = 0; r < s; ++r) {
+            int64_t a, b2 = ignore_label;
+            if (vec) ldg_i64x2(base + (int64_t)r * W + x0, a, b2);
+            else a = ldg_i64(base + (int64_t)r * W + x0);
+            int la = (a == ignore_label) ? C : (int)a;
+            int lb = (b2 == ignore_label) ? C : (int)b2;
+            bad |= (a != ignore_label && (a < 0 || a >= C)) || (b2 != ignore_label && (b2 < 0 || b2 >= C));
+#pragma unroll
+            for (int ci = 0; ci <= C; ++ci) { cnt0[ci] += (la == ci); cnt1[ci] += (lb == ci); }
+        }
+        const int c0 = x0 / s, c1 = (x0 + 1) / s;
+        if (two && c1 == c0) {
+#pragma unroll
+            for (int ci = 0; ci <= C; ++ci) { unsigned v = cnt0[ci] + cnt1[ci]; if (v) atomicAdd(&bins[c0 * (C + 1) + ci], v); }
+        } else {
+#pragma unroll
+            for (int ci = 0; ci <= C; ++ci) {
+                if (cnt0[ci]) atomicAdd(&bins[c0 * (C + 1) + ci], cnt0[ci]);
+                if (two && cnt1[ci]) atomicAdd(&bins[c1 * (C + 1) + ci], cnt1[ci]);
+            }
+        }
+    }
+    if (bad && status) atomicOr(status, 1);
+    __syncthreads();
+    const float area = (float)(s * s);
+    for (int cx = threadIdx.x; cx < w; cx += blockDim.x) {
+        const unsigned* bn = bins + cx * (C + 1);
+        unsigned best = bn[0];
+        int arg = 0;
+#pragma unroll
+        for (int ci = 1; ci <= C; ++ci)
+            if (bn[ci] > best) { best = bn[ci]; arg = ci; }  // first index wins ties (torch.max)
+        const float ratio = __fdiv_rn((float)best, area);   // avg_pool2d of the one-hot: count / (s*s)
+        int64_t o = (arg == C || ratio < min_ratio) ? ignore_label : (int64_t)arg;
+        out[((int64_t)bi * h + oy) * w + cx] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------- prototype sums
+constexpr int kAccThreads = 256;  // 8 warps = 8 channel rows per CTA
+
+// stage the class ids of image bi as bytes (255 = ignore / out of range)
+__device__ __forceinline__ void stage_labels(unsigned char* lab, const int64_t* __restrict__ label, int64_t hw, int c,
+                                             int64_t ignore_label) {
+    for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) {
+        int64_t v = label[i];
+        lab[i] = (v >= 0 && v < c && v != ignore_label) ? (unsigned char)v : (unsigned char)255;
+    }
+}
+
+// partial[(bi*C + ci)*k + kk] = sum over pixels of image bi with label ci of feat[bi,kk,:]
+template <int C, int VEC>
+__global__ void __launch_bounds__(kAccThreads) proto_accum_kernel(const float* __restrict__ feat, int k, int64_t hw,
+                                                                  const int64_t* __restrict__ label, int64_t ignore_label,
+                                                                  float* __restrict__ partial, int* __restrict__ cnt_partial) {
+    extern __shared__ unsigned char lab[];
+    const int bi = blockIdx.y;
+    stage_labels(lab, label + (int64_t)bi * hw, hw, C, ignore_label);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0) {  // class counts of this image, once
+        for (int ci = warp; ci < C; ci += kAccThreads / 32) {
+            int n = 0;
+            for (int64_t i = lane; i < hw; i += 32) n += (lab[i] == ci);
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (lane == 0) cnt_partial[bi * C + ci] = n;
+        }
+    }
+    const int kk = blockIdx.x * (kAccThreads / 32) + warp;
+    if (kk >= k) return;
+    const float* f = feat + ((int64_t)bi * k + kk) * hw;
+    float acc[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) acc[ci] = 0.f;
+    const int64_t groups = hw / VEC;
+#pragma unroll 4
+    for (int64_t g = lane; g < groups; g += 32) {
+        PixVec<VEC> v;
+        v.load(f + g * VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int l = lab[g * VEC + i];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) acc[ci] += (l == ci) ? v.v[i] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+        float x = warp_sum(acc[ci]);
+        if (lane == 0) partial[((int64_t)bi * C + ci) * k + kk] = x;
+    }
+}
+
+// soft weights: bilinear (align_corners=True) down-sampling of soft (b,C,H,W) to (h,w) (alignment.py:102)
+__global__ void __launch_bounds__(256) soft_down_kernel(const float* __restrict__ soft, int planes, int H, int W, int h, int w,
+                                                        float sy, float sx, float* __restrict__ down) {
+    const int64_t total = (int64_t)planes * h * w;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int x = (int)(i % w);
+        const int y = (int)((i / w) % h);
+        const int64_t pl = i / ((int64_t)w * h);
+        const Lerp ly = make_lerp(y, H, sy), lx = make_lerp(x, W, sx);
+        const float* p = soft + pl * H * W;
+        const float top = lx.l0 * p[(int64_t)ly.i0 * W + lx.i0] + lx.l1 * p[(int64_t)ly.i0 * W + lx.i1];
+        const float bot = lx.l0 * p[(int64_t)ly.i1 * W + lx.i0] + lx.l1 * p[(int64_t)ly.i1 * W + lx.i1];
+        down[i] = ly.l0 * top + ly.l1 * bot;
+    }
+}
+
+// partial[(bi*C + ci)*k + kk] = sum_px feat[bi,kk,px] * down[bi,ci,px]
+template <int C, int VEC>
+__global__ void __launch_bounds__(kAccThreads) proto_accum_soft_kernel(const float* __restrict__ feat, int k, int64_t hw,
+                                                                       const float* __restrict__ down, float* __restrict__ partial) {
+    const int bi = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = blockIdx.x * (kAccThreads / 32) + warp;
+    if (kk >= k) return;
+    const float* f = feat + ((int64_t)bi * k + kk) * hw;
+    const float* wd = down + (int64_t)bi * C * hw;
+    float acc[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) acc[ci] = 0.f;
+    const int64_t groups = hw / VEC;
+    for (int64_t g = lane; g < groups; g += 32) {
+        PixVec<VEC> v;
+        v.load(f + g * VEC);
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[ci] = fmaf(v.v[i], __ldg(wd + (int64_t)ci * hw + g * VEC + i), acc[ci]);
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+        float x = warp_sum(acc[ci]);
+        if (lane == 0) partial[((int64_t)bi * C + ci) * k + kk] = x;
+    }
+}
+
+// fold the per-image partials in image order (deterministic)
+__global__ void __launch_bounds__(256) proto_fold_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial,
+                                                         int b, int ck, int c, float* __restrict__ sums, int64_t* __restrict__ counts) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < ck) {
+        float s = 0.f;
+        for (int bi = 0; bi < b; ++bi) s += partial[(int64_t)bi * ck + i];
+        sums[i] = s;
+    }
+    if (counts && cnt_partial && i < c) {
+        int64_t n = 0;
+        for (int bi = 0; bi < b; ++bi) n += cnt_partial[bi * c + i];
+        counts[i] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256) proto_finalize_kernel(const float* __restrict__ sums, const int64_t* __restrict__ counts,
+                                                             const float* __restrict__ proto_old, int c, int k, float eps,
+                                                             float one_minus_decay, float decay, int64_t mean_n,
+                                                             float* __restrict__ local_out, float* __restrict__ proto_new) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= c * k) return;
+    const int ci = i / k;
+    float local;
+    if (counts) {
+        const int64_t n = counts[ci];
+        local = sums[i] / ((float)n + eps);                 // alignment.py:348
+        if (n < 1) local = proto_old[i];                    // :350 classes without samples keep the old prototype
+    } else {
+        local = sums[i] / (float)mean_n;                    // torch.mean over n pixels, alignment.py:104
+    }
+    if (local_out) local_out[i] = local;
+    if (proto_new)                                          // _ema, alignment.py:465: two rounded products, one rounded sum
+        proto_new[i] = __fadd_rn(__fmul_rn(one_minus_decay, local), __fmul_rn(decay, proto_old[i]));
+}
+
+}  // namespace
+
+extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W, int scale, int n_classes, int64_t ignore_label,
+                                       float min_ratio, int64_t* out, int32_t* status, void* stream) {
+    UEM_REQUIRE(label && out && b > 0 && H > 0 && W > 0, "uem_downscale_label_i64: bad arguments");
+    UEM_REQUIRE(scale > 1, "uem_downscale_label_i64: scale_factor must be > 1");  // alignment.py:488
+    const int h = H / scale, w = W / scale;
+    if (h == 0 || w == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec = (W % 2 == 0) && uem_aligned16(label) && (scale % 2 == 0);
+    const int cols = vec ? (w * scale + 1) / 2 : w * scale;
+    const int threads = min(512, max(32, ((cols + 31) / 32) * 32));
+    UEM_DISPATCH_C(n_classes, {
+        size_t smem = (size_t)w * (C + 1) * sizeof(unsigned);
+        UEM_REQUIRE(smem <= 48 * 1024, "uem_downscale_label_i64: output width %d too large", w);
+        dim3 grid(h, b);
+        downscale_kernel<C><<<grid, threads, smem, st>>>(label, H, W, scale, h, w, ignore_label, min_ratio, vec, out, status);
+    });
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+// ws layout: [partial b*c*k f32][cnt_partial b*c i32]; the soft variant appends [down b*c*h*w f32]
+extern "C" int64_t uem_proto_accum_ws_bytes(int b, int c, int k) {
+    return (((int64_t)b * c * k + (int64_t)b * c + 4) * 4 + 15) & ~(int64_t)15;
+}
+extern "C" int64_t uem_proto_accum_soft_ws_bytes(int b, int c, int k, int h, int w) {
+    return uem_proto_accum_ws_bytes(b, c, k) + (int64_t)b * c * h * w * 4;
+}
+
+extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t hw, const int64_t* label, int c,
+                                        int64_t ignore_label, float* sums, int64_t* counts, void* ws, void* stream) {
+    UEM_REQUIRE(feat && label && sums && counts && ws && b > 0 && k > 0 && hw > 0, "uem_proto_accum_nchw_f32: bad arguments");
+    UEM_REQUIRE(hw <= 200 * 1024, "uem_proto_accum_nchw_f32: %lld feature pixels per image exceed the shared-memory label stage", (long long)hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = (float*)ws;
+    int* cnt_partial = (int*)(partial + (int64_t)b * c * k);
+    const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
+    const size_t smem = (size_t)((hw + 15) / 16) * 16;
+    UEM_DISPATCH_C(c, {
+        dim3 grid(uem_div_up(k, kAccThreads / 32), b);
+        if (vec) {
+            if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(proto_accum_kernel<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            proto_accum_kernel<C, 4><<<grid, kAccThreads, smem, st>>>(feat, k, hw, label, ignore_label, partial, cnt_partial);
+        } else {
+            if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(proto_accum_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            proto_accum_kernel<C, 1><<<grid, kAccThreads, smem, st>>>(feat, k, hw, label, ignore_label, partial, cnt_partial);
+        }
+    });
+    proto_fold_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, st>>>(partial, cnt_partial, b, c * k, c, sums, counts);
+    UEM_CHECK_LAUNCH_N(2);
+    return 0;
+}
+
+extern "C" int uem_proto_accum_soft_f32(const float* feat, int b, int k, int h, int w, const float* soft, int c, int H, int W,
+                                        float* sums, void* ws, void* stream) {
+    UEM_REQUIRE(feat && soft && sums && ws && b > 0 && k > 0 && h > 0 && w > 0, "uem_proto_accum_soft_f32: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t hw = (int64_t)h * w;
+    float* partial = (float*)ws;
+    float* down = (float*)((char*)ws + uem_proto_accum_ws_bytes(b, c, k));
+    const float sy = uem_align_corners_scale(H, h), sx = uem_align_corners_scale(W, w);
+    const int64_t total = (int64_t)b * c * hw;
+    soft_down_kernel<<<(int)min((int64_t)UEM_SMS * 8, (total + 255) / 256), 256, 0, st>>>(soft, b * c, H, W, h, w, sy, sx, down);
+    const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
+    UEM_DISPATCH_C(c, {
+        dim3 grid(uem_div_up(k, kAccThreads / 32), b);
+        if (vec) proto_accum_soft_kernel<C, 4><<<grid, kAccThreads, 0, st>>>(feat, k, hw, down, partial);
+        else proto_accum_soft_kernel<C, 1><<<grid, kAccThreads, 0, st>>>(feat, k, hw, down, partial);
+    });
+    proto_fold_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, st>>>(partial, nullptr, b, c * k, c, sums, nullptr);
+    UEM_CHECK_LAUNCH_N(3);
+    return 0;
+}
+
+extern "C" int uem_proto_finalize_ema_f32(const float* sums, const int64_t* counts, int64_t mean_n, const float* proto_old, int c,
+                                          int k, float eps, float one_minus_decay, float decay, float* local_out,
+                                          float* proto_new, void* stream) {
+    UEM_REQUIRE(sums && proto_old && c > 0 && k > 0 && (local_out || proto_new), "uem_proto_finalize_ema_f32: bad arguments");
+    UEM_REQUIRE(counts || mean_n > 0, "uem_proto_finalize_ema_f32: need counts or mean_n");
+    proto_finalize_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, (cudaStream_t)stream>>>(
+        sums, counts, proto_old, c, k, eps, one_minus_decay, decay, mean_n, local_out, proto_new);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}

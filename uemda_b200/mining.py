@@ -1,0 +1,160 @@
+"""The fused mining step and its batch-sharded multi-GPU form.
+
+``refine_select`` is one C-ABI call (uem_mine_refine_select_f32) that enqueues, with no host sync,
+    [batch max superpixel id] -> [region max of soft] -> [Pearson 1/dist at feature res] ->
+    [fused full-res refine (+ per-class max partials)] -> [pseudo-label selection]
+which is tools/train_ssl_uem.py:209-214 / vis_corrected_pseudo_labels.py:185-189 of the reference.
+
+``ShardedMiner`` shards the target batch (or tile list) over the ranks of a torch.distributed job
+(one process per GPU).  Per-pixel / per-image / per-region work is rank-local; only
+  * the batch-global max superpixel id (alignment.py:241)           -> all_reduce(MAX), 8 B
+  * prototype partial sums (c,k) + counts (c) (alignment.py:347-353) -> all_reduce(SUM), <= 57 KiB
+  * class histogram (c+1) (balance.py:49-52)                         -> all_reduce(SUM), 64 B
+cross the NVLink fabric.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pred2=None, sup=None, num_regions=None,
+                  ignored_id=None, eps=1e-7, select=None, ws=None):
+    """Returns (refined (b,c,H,W) fp32, hard (b,H,W) int64 or None).
+
+    select: None or (cutoff_top, cutoff_low, ignore_label).
+    num_regions: capacity R of the region table (ids must lie in [0,R)); None -> read sup.max() back
+        (one 8-byte device->host copy, like torch_scatter's ``int(index.max())+1``).
+    ignored_id: optional (1,) int64 device tensor holding the batch-global max id (e.g. after an
+        all_reduce(MAX) across ranks); None -> computed from ``sup`` inside the call."""
+    L.require_cuda(soft, feat, prototypes, pred1, pred2, sup, ignored_id)
+    soft = L.f32c(soft.detach())
+    b, c, H, W = soft.shape
+    lib = L.bind(soft)
+    k = h = w = 0
+    if views & ops.VIEW_PROTO:
+        feat = L.f32c(feat.detach())
+        prototypes = L.f32c(prototypes.detach())
+        _, k, h, w = feat.shape
+        assert prototypes.shape == (c, k), "prototypes must be (class_num, feat_channels)"
+    if views & ops.VIEW_PRED:
+        pred1 = L.f32c(pred1.detach())
+        pred2 = None if pred2 is None else L.f32c(pred2.detach())
+        if h:
+            assert pred1.shape[-2:] == (h, w), "feature map and logits must share their resolution"
+        h, w = pred1.shape[-2:]
+    R = 0
+    if views & ops.VIEW_SUP:
+        sup = L.i64c(sup.detach())
+        assert sup.numel() == b * H * W
+        if num_regions is None:
+            mm = ops.i64_minmax(sup)
+            R = int(mm[1].item()) + 1
+            if ignored_id is None:
+                ignored_id = mm[1:]
+        else:
+            R = int(num_regions)
+    need = lib.uem_mine_ws_bytes(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
+    if ws is None or ws.numel() < need:
+        ws = L.workspace(need, soft)
+        ws[:32].zero_()
+    refined = torch.empty_like(soft)
+    hard = None
+    top = low = 0.0
+    ign = -1
+    if select is not None:
+        top, low, ign = select
+        hard = torch.empty((b, H, W), dtype=torch.int64, device=soft.device)
+    L.check(lib.uem_mine_refine_select_f32(
+        int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
+        L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
+        L.ptr(hard), L.ptr(ws), L.stream_of(soft)))
+    # per-CTA [class maxima | min] of `refined`, reused by pseudo_selection() so it needs no second max pass
+    nparts = lib.uem_label_refine_partials(H)
+    off = need - ((b * nparts * (c + 1) * 4 + 15) // 16) * 16
+    partial = ws[off:off + b * nparts * (c + 1) * 4].view(torch.float32).view(b, nparts, c + 1)
+    refined._uem_partials = (partial, refined._version)
+    refined._uem_ws = ws
+    return refined, hard
+
+
+def mine_step(aligner, label_t_sup, feat_t, preds_t, label_t_soft, mode="all", temp=2.0, cutoff_top=0.8, cutoff_low=0.6,
+              ignore_label=-1, ws=None):
+    """label_refine + pseudo_selection of one target batch as a single fused call (no host sync when
+    aligner.num_regions is set).  Returns (label_t_soft_refined, label_t_hard)."""
+    views = ops.MODE_VIEWS[mode]
+    pred1, pred2 = (preds_t if isinstance(preds_t, (list, tuple)) else (preds_t, None))
+    return refine_select(views, label_t_soft, temp, feat=feat_t, prototypes=aligner.prototypes, pred1=pred1, pred2=pred2,
+                         sup=label_t_sup, num_regions=aligner.num_regions, eps=aligner.eps,
+                         select=(cutoff_top, cutoff_low, ignore_label), ws=ws)
+
+
+# ----------------------------------------------------------------------------------------------------
+# multi-GPU: batch sharding, tiny all-reduces only
+# ----------------------------------------------------------------------------------------------------
+def shard_range(n_items, rank, world_size):
+    """Contiguous slice [lo,hi) of n_items owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_stats(sums, counts, hist=None):
+    """[c*k sums | c counts | c+1 hist] as one fp64 vector (exact for the integer parts) for a single all_reduce."""
+    parts = [sums.reshape(-1).double(), counts.reshape(-1).double()]
+    if hist is not None:
+        parts.append(hist.reshape(-1).double())
+    return torch.cat(parts)
+
+
+def unpack_stats(buf, c, k, with_hist):
+    sums = buf[:c * k].float().reshape(c, k)
+    counts = buf[c * k:c * k + c].round().long()
+    hist = buf[c * k + c:c * k + 2 * c + 1].round().long() if with_hist else None
+    return sums, counts, hist
+
+
+class ShardedMiner:
+    """Runs the mining step on this rank's shard of a global batch and keeps the replicated state
+    (prototype bank, class-frequency EMA) identical on every rank."""
+
+    def __init__(self, aligner, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.aligner = aligner
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def global_ignored_id(self, sup_local):
+        """all_reduce(MAX) of the local max superpixel id -> (1,) int64 device tensor (alignment.py:241)."""
+        mx = ops.i64_minmax(sup_local)[1:].clone()
+        if self.world > 1:
+            self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX, group=self.group)
+        return mx
+
+    def mine(self, sup_local, feat_local, preds_local, soft_local, mode="all", temp=2.0, cutoff_top=0.8, cutoff_low=0.6,
+             ignore_label=-1, num_regions=None):
+        views = ops.MODE_VIEWS[mode]
+        ignored = None
+        if views & ops.VIEW_SUP:
+            ignored = self.global_ignored_id(sup_local)
+            if num_regions is None:
+                num_regions = int(ignored.item()) + 1
+        pred1, pred2 = (preds_local if isinstance(preds_local, (list, tuple)) else (preds_local, None))
+        return refine_select(views, soft_local, temp, feat=feat_local, prototypes=self.aligner.prototypes, pred1=pred1,
+                             pred2=pred2, sup=sup_local, num_regions=num_regions, ignored_id=ignored, eps=self.aligner.eps,
+                             select=(cutoff_top, cutoff_low, ignore_label))
+
+    def update_prototype(self, feat_local, label_local):
+        """Aligner.update_prototype over the global batch: local masked sums -> all_reduce(SUM) -> EMA."""
+        al = self.aligner
+        down = al.downscale_gt(label_local)
+        sums, counts = ops.proto_accumulate(feat_local, down, al.class_num, al.ignore_label)
+        if self.world > 1:
+            buf = pack_stats(sums, counts)
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+            sums, counts, _ = unpack_stats(buf, al.class_num, sums.shape[1], False)
+        _, new = ops.proto_finalize(sums, counts, al.prototypes, eps=al.eps, decay=al.decay, want_local=False)
+        al.prototypes = new
+        return down
