@@ -229,18 +229,27 @@ def main():
     miner = mining.ShardedMiner(al) if world > 1 else None
     ws = None
 
+    side = torch.cuda.Stream(device=dev)
+
     def step_resident(s):
-        """device-resident step, no host sync (strict asserts off)"""
+        """device-resident step, no host sync (strict asserts off).  The source-side chain (DownscaleLabel ->
+        masked prototype sums -> EMA) is independent of the target-side chain until the next step, so it runs on a
+        second stream; the EMA result is only published after the target chain has read the old prototypes."""
         nonlocal ws
+        cur = torch.cuda.current_stream(dev)
+        protos = al.prototypes
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if miner:
+                miner.update_prototype(s["feat_s"], s["label_s"])
+            else:
+                al.update_prototype(s["feat_s"], s["label_s"])
         ignored = miner.global_ignored_id(s["sup"]) if miner else None
-        refined, hard = mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=al.prototypes, pred1=s["pred1"],
-                                             pred2=s["pred2"], sup=s["sup"], num_regions=R, ignored_id=ignored, eps=al.eps,
-                                             select=(CUTOFF[0], CUTOFF[1], -1), ws=ws)
-        if miner:
-            miner.update_prototype(s["feat_s"], s["label_s"])
-        else:
-            al.update_prototype(s["feat_s"], s["label_s"])
-        ent, wgt = ops.entropy_uvem_weight(refined, *UVEM)
+        refined, hard, ent, wgt = mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=protos,
+                                                       pred1=s["pred1"], pred2=s["pred2"], sup=s["sup"], num_regions=R,
+                                                       ignored_id=ignored, eps=al.eps, select=(CUTOFF[0], CUTOFF[1], -1),
+                                                       ws=ws, uvem=UVEM)
+        cur.wait_stream(side)
         return refined, hard, ent, wgt
 
     def barrier():

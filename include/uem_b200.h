@@ -94,6 +94,21 @@ UEM_API int uem_pseudo_select_f32(const float* mask, const float* cmax, int b, i
                           float cutoff_top, float cutoff_low, int64_t ignore_label, int variant,
                           int64_t* out, void* stream);
 
+/* Class statistics table raised atomically by uem_label_refine_f32: (b, c+2) uint32 =
+ * [c order-preserving encodings of the per-class maxima | encoding of -(image minimum) | bad flag (NaN/inf seen)].
+ * The caller zeroes it (uem_class_stats_bytes bytes) before the refine call; 0 = untouched slot.
+ * uem_select_entropy_stats_f32: a5 (variant 0) fed by that table (no second pass for the class max), plus,
+ * optionally, a2 + a3 of the same map in the same pass: entropy (b*hw) and UVEM weight (b*hw).
+ * uvem_host: NULL or HOST pointer to {m, t, 1/gamma, coef_left, coef_right}.
+ * uem_class_stats_decode_f32: table -> cmax (b*c) and image_min (b) as plain floats (NaN if the bad flag is set),
+ * for the reference's range assert (pseudo_generation.py:71). */
+UEM_API int64_t uem_class_stats_bytes(int b, int c);
+UEM_API int uem_select_entropy_stats_f32(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw,
+                                 float cutoff_top, float cutoff_low, int64_t ignore_label, int64_t* out,
+                                 const float* uvem_host, float* entropy, float* weight, void* stream);
+UEM_API int uem_class_stats_decode_f32(const uint32_t* class_stats, int b, int c, float* cmax, float* image_min,
+                               void* stream);
+
 /* ---- a6s/a7 seam: torch_scatter.scatter over superpixel ids -----------------------------
  * alignment.py:187 (sum, int64) and :245 (max, f32).  src element (bi,n,ci) lives at
  * src[bi*src_sb + n*src_sn + ci*src_sc] (element strides: (b,N,c) contiguous = {N*c,c,1};
@@ -139,31 +154,31 @@ UEM_API int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, cons
  * pred1/pred2 (b,c,h,w) logits (pred2 may be NULL) (PRED view); sup (b,H,W) int64 + region_max
  * (b,R,c) from uem_region_reduce_f32(MAX) + ignored_id (device pointer to the batch-global max id,
  * alignment.py:241) (SUP view).  soft (b,c,H,W) -> out (b,c,H,W).
- * class_max_partial (optional, may be NULL): per-CTA maxima of `out`, layout
- * (b, uem_label_refine_partials(H), c+1) = [c per-class maxima | overall minimum] (NaN-poisoned if the
- * CTA produced a NaN), consumed by uem_pseudo_select_partials_f32. */
-UEM_API int uem_label_refine_partials(int H);
+ * class_stats (optional, may be NULL): the (b, c+2) statistics table of `out` described above, zeroed by the
+ * caller, consumed by uem_select_entropy_stats_f32.
+ * ws: uem_label_refine_ws_bytes(b,c,R) bytes (per-region weights of the SUP view; may be NULL without it). */
+UEM_API int64_t uem_label_refine_ws_bytes(int b, int c, int64_t R);
 UEM_API int uem_label_refine_f32(int views, const float* simi, const float* pred1, const float* pred2, int h,
                          int w, const int64_t* sup, const float* region_max, int64_t R,
                          const int64_t* ignored_id, const float* soft, int b, int c, int H, int W,
-                         float temp, float* out, float* class_max_partial, void* stream);
-/* a5 fed by the partial maxima written by uem_label_refine_f32 (no second pass for the class max) */
-UEM_API int uem_pseudo_select_partials_f32(const float* mask, const float* class_max_partial, int n_partials,
-                                   int b, int c, int64_t hw, float cutoff_top, float cutoff_low,
-                                   int64_t ignore_label, int64_t* out, void* stream);
+                         float temp, float* out, uint32_t* class_stats, void* ws, void* stream);
 
 /* ---- fused chain: label_refine -> pseudo_selection in one call, no host sync -----------------
  * tools/train_ssl_uem.py:209-214 (vis_corrected_pseudo_labels.py:185-189).  feat (b,k,h,w), protos (c,k),
  * pred1/pred2 (b,c,h,w), sup (b,H,W) with ids in [0,R) (R = capacity of the region table, >= max id+1),
  * ignored_id: device pointer to the batch-global max id or NULL (then computed from sup, alignment.py:241),
- * soft (b,c,H,W) -> refined (b,c,H,W), hard (b,H,W) int64 (NULL = skip the selection).
- * ws: uem_mine_ws_bytes(...) bytes; ws[0..3] int32 status word: bit 2 = superpixel id outside [0,R). */
+ * soft (b,c,H,W) -> refined (b,c,H,W), hard (b,H,W) int64 (NULL = skip the selection); with hard, optionally the
+ * entropy (b,H,W) and UVEM weight (b,H,W) of the refined map (balance.py:372,396-423; uvem_host as above).
+ * ws: uem_mine_ws_bytes(...) bytes; ws[0..3] int32 status word: bit 2 = superpixel id outside [0,R);
+ * the class statistics table of `refined` is left at byte offset uem_mine_ws_stats_offset(...) of ws. */
 UEM_API int64_t uem_mine_ws_bytes(int b, int c, int H, int W, int h, int w, int k, int64_t R);
+UEM_API int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R);
 UEM_API int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos,
                                const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                                int64_t R, const int64_t* ignored_id, const float* soft, int b, int c, int H,
                                int W, float temp, float eps, float cutoff_top, float cutoff_low,
-                               int64_t ignore_label, float* refined, int64_t* hard, void* ws, void* stream);
+                               int64_t ignore_label, float* refined, int64_t* hard, const float* uvem_host,
+                               float* entropy, float* weight, void* ws, void* stream);
 
 /* ---- a13: Aligner.get_prototype_weight_4pixel, alignment.py:295-309 --------------------- */
 UEM_API int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, const int64_t* hard, int b, int c,

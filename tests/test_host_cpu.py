@@ -46,7 +46,7 @@ def test_ctypes_signatures_match_header(built_lib):
     lib = _lib.load()  # loading needs no GPU
     assert lib.uem_version() == 1
     # pure host helpers can be called without a device
-    assert lib.uem_label_refine_partials(512) == 128
+    assert lib.uem_class_stats_bytes(8, 6) >= 8 * 8 * 4
     assert lib.uem_class_max_ws_bytes(8, 6, 512 * 512) > 0
     assert lib.uem_mine_ws_bytes(8, 6, 512, 512, 32, 32, 2048, 1025) > 8 * 6 * 32 * 32 * 4
 

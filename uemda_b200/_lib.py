@@ -32,7 +32,6 @@ SIGNATURES = {
     "uem_class_max_ws_bytes": (_L, [_I, _I, _L]),
     "uem_class_max_f32": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P]),
     "uem_pseudo_select_f32": (_I, [_P, _P, _I, _I, _L, _F, _F, _L, _I, _P, _P]),
-    "uem_pseudo_select_partials_f32": (_I, [_P, _P, _I, _I, _I, _L, _F, _F, _L, _P, _P]),
     "uem_i64_minmax": (_I, [_P, _L, _P, _P]),
     "uem_region_reduce_ws_bytes": (_L, [_I, _L, _I]),
     "uem_region_reduce_f32": (_I, [_P, _L, _L, _L, _P, _I, _L, _I, _L, _I, _P, _P, _P]),
@@ -43,11 +42,15 @@ SIGNATURES = {
     "uem_pearson_ws_bytes": (_L, [_I, _I]),
     "uem_pearson_dist_nchw_f32": (_I, [_P, _I, _I, _L, _P, _I, _F, _I, _P, _P, _P]),
     "uem_pearson_dist_rows_f32": (_I, [_P, _L, _I, _P, _I, _F, _P, _P, _P]),
-    "uem_label_refine_partials": (_I, [_I]),
-    "uem_label_refine_f32": (_I, [_I, _P, _P, _P, _I, _I, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "uem_label_refine_ws_bytes": (_L, [_I, _I, _L]),
+    "uem_label_refine_f32": (_I, [_I, _P, _P, _P, _I, _I, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "uem_class_stats_bytes": (_L, [_I, _I]),
+    "uem_select_entropy_stats_f32": (_I, [_P, _P, _I, _I, _L, _F, _F, _L, _P, _P, _P, _P, _P]),
+    "uem_class_stats_decode_f32": (_I, [_P, _I, _I, _P, _P, _P]),
     "uem_mine_ws_bytes": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
+    "uem_mine_ws_stats_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_refine_select_f32": (_I, [_I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F,
-                                        _L, _P, _P, _P, _P]),
+                                        _L, _P, _P, _P, _P, _P, _P, _P]),
     "uem_proto_weight_4pixel_f32": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _L, _F, _P, _P]),
     "uem_proto_accum_ws_bytes": (_L, [_I, _I, _I]),
     "uem_proto_accum_soft_ws_bytes": (_L, [_I, _I, _I, _I, _I]),

@@ -88,6 +88,14 @@ __device__ __forceinline__ unsigned ld_cg_u32(const unsigned* p) {
     return r;
 }
 
+// cp.async (LDGSTS): global -> shared without staging registers
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // VEC pixels per thread (4 = 128-bit path, 1 = scalar fallback for unaligned / ragged rows)
 template <int VEC> struct PixVec;
 template <> struct PixVec<4> {
@@ -200,22 +208,35 @@ template <int C> __device__ __forceinline__ void peak_norm_regs(float (&x)[C]) {
 
 // UVEMLoss.get_weight (balance.py:396-423), operation by operation (no FMA contraction)
 __device__ __forceinline__ float uvem_weight_dev(float u, float m, float t, float inv_gamma, float cl, float cr) {
-    float wl = 1.0f;
-    if (m > 0.f) {
-        float x = (u <= m && u >= 0.f) ? u : 1.0f;
-        float d = __fsub_rn(x, m);
-        x = __fadd_rn(__fmul_rn(cl, __fmul_rn(d, d)), 1.0f);
-        x = fminf(fmaxf(x, 0.f), 1.f);
-        wl = powf(x, inv_gamma);
+    // only the branch that the final where() selects is evaluated; NaN fails every comparison and lands on the
+    // right branch with the substitute value 0, exactly like the reference
+    const bool left = (u <= m);
+    const bool enabled = left ? (m > 0.f) : (m < t);
+    const float sub = left ? ((u >= 0.f) ? u : 1.0f) : ((u > m && u <= t) ? u : 0.0f);
+    const float d = __fsub_rn(sub, m);
+    float x = __fadd_rn(__fmul_rn(left ? cl : cr, __fmul_rn(d, d)), 1.0f);
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    // x^(1/gamma) = 2^(lg2(x)/gamma): lg2.approx is 2^-22 absolute on [0.5,2] and 2 ulp elsewhere, 1/gamma <= 1
+    // keeps the result within ~1e-6 relative of the reference's pow; x = 0 -> 0, x = 1 -> 1 exactly
+    float w = __powf(x, inv_gamma);
+    if (!enabled) w = left ? 1.0f : 0.0f;
+    return (u >= t) ? 0.f : w;
+}
+
+// entropy sum_c -p log p (balance.py:372).  The cheap log (lg2.approx, 2 ulp for p < 0.5) is used except for the
+// (at most one) class with p >= 0.5, where its 2^-22 absolute error would dominate a small -p log p: that one
+// gets the accurate logf.  p == 0 yields NaN exactly like the reference.
+template <int C>
+__device__ __forceinline__ float entropy_px(const float (&p)[C]) {
+    float u = 0.f, vmax = p[0];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+        const float v = p[ci];
+        vmax = fmaxf(vmax, v);
+        u += (-v) * __logf(v);
     }
-    float wr = 0.f;
-    if (m < t) {
-        float x = (u > m && u <= t) ? u : 0.0f;
-        float d = __fsub_rn(x, m);
-        x = __fadd_rn(__fmul_rn(cr, __fmul_rn(d, d)), 1.0f);
-        x = fminf(fmaxf(x, 0.f), 1.f);
-        wr = powf(x, inv_gamma);
-    }
-    float wgt = (u <= m) ? wl : wr;
-    return (u >= t) ? 0.f : wgt;
+    // one accurate log per pixel, control flow uniform across the warp: swap the fast term of the largest
+    // class for the accurate one when it matters (p_max >= 0.5; NaN/zero patterns are untouched)
+    const float fix = (-vmax) * (logf(vmax) - __logf(vmax));
+    return (vmax >= 0.5f) ? u + fix : u;
 }

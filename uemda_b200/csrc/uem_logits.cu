@@ -110,16 +110,17 @@ __global__ void __launch_bounds__(256) entropy_weight_kernel(const float* __rest
     if (g * VEC < hw) {
         const int64_t px = g * VEC;
         const float* base = soft + (int64_t)bi * C * hw + px;
-        float u[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) u[i] = 0.f;
+        float pv[VEC][C];
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) {
             PixVec<VEC> v;
             v.load(base + (int64_t)ci * hw);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) u[i] += (-v.v[i]) * logf(v.v[i]);
+            for (int i = 0; i < VEC; ++i) pv[i][ci] = v.v[i];
         }
+        float u[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) u[i] = entropy_px<C>(pv[i]);
         const int64_t o = (int64_t)bi * hw + px;
         if (entropy) { PixVec<VEC> e; for (int i = 0; i < VEC; ++i) e.v[i] = u[i]; e.store(entropy + o); }
         if (weight) {

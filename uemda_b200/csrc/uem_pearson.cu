@@ -13,12 +13,14 @@
 namespace {
 
 constexpr int kPearsonThreads = 256;
-constexpr int kSlices = 32;    // k-slices per CTA
-constexpr int kPxLanes = 8;    // lanes along pixels; each handles VEC pixels
+constexpr int kPxLanes = 4;    // lanes along pixels; each handles VEC pixels (64 B of a channel row per warp quarter)
+constexpr int kSlices = kPearsonThreads / kPxLanes;  // k-slices per CTA (64): 512 CTAs of 16 pixels at config 2
+constexpr int kDepth = 8;      // cp.async ring depth per thread
+constexpr int kPcStride = 8;   // transposed centred prototypes: pcT[kk][8] -> two LDG.128 fetch all classes of a channel
 
 // centre the prototypes once: pc (m,k), stats[j] = {std_j (unbiased), sum_k pc_j}
-__global__ void __launch_bounds__(256) proto_center_kernel(const float* __restrict__ protos, int k, float* __restrict__ pc,
-                                                           float* __restrict__ stats) {
+__global__ void __launch_bounds__(256) proto_center_kernel(const float* __restrict__ protos, int k, int transposed,
+                                                           float* __restrict__ pc, float* __restrict__ stats) {
     const int j = blockIdx.x;
     const float* p = protos + (int64_t)j * k;
     __shared__ float red[8];
@@ -34,7 +36,8 @@ __global__ void __launch_bounds__(256) proto_center_kernel(const float* __restri
     float s2 = 0.f, s1 = 0.f;
     for (int i = threadIdx.x; i < k; i += 256) {
         float d = p[i] - mean;
-        pc[(int64_t)j * k + i] = d;
+        if (transposed) pc[(int64_t)i * kPcStride + j] = d;
+        else pc[(int64_t)j * k + i] = d;
         s2 += d * d;
         s1 += d;
     }
@@ -67,7 +70,7 @@ __device__ __forceinline__ float pearson_finish(float S1, float S2, float Cj, fl
 
 // feat (b,k,hw) planar -> out (b,M,hw) planar
 template <int M, int VEC>
-__global__ void __launch_bounds__(kPearsonThreads) pearson_nchw_kernel(const float* __restrict__ feat, int k, int64_t hw,
+__global__ void __launch_bounds__(kPearsonThreads, 4) pearson_nchw_kernel(const float* __restrict__ feat, int k, int64_t hw,
                                                                        const float* __restrict__ pc, const float* __restrict__ stats,
                                                                        float eps, int reciprocal, float* __restrict__ out) {
     constexpr int NA = 2 + M;
@@ -87,13 +90,14 @@ __global__ void __launch_bounds__(kPearsonThreads) pearson_nchw_kernel(const flo
     if (active) {
         PixVec<VEC> piv;
         piv.load(f);  // channel 0 of these pixels: the shift that keeps the one-pass variance stable
-#pragma unroll 4
-        for (int kk = ks; kk < k; kk += kSlices) {
-            PixVec<VEC> v;
-            v.load(f + (int64_t)kk * hw);
-            float pcv[M];
-#pragma unroll
-            for (int j = 0; j < M; ++j) pcv[j] = __ldg(pc + (int64_t)j * k + kk);
+        auto consume = [&](const PixVec<VEC>& v, int kk) {
+            float pcv[kPcStride];
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pc + (int64_t)kk * kPcStride));
+            pcv[0] = a.x; pcv[1] = a.y; pcv[2] = a.z; pcv[3] = a.w;
+            if (M > 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(pc + (int64_t)kk * kPcStride) + 1);
+                pcv[4] = c4.x; pcv[5] = c4.y; pcv[6] = c4.z; pcv[7] = c4.w;
+            }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 const float g = v.v[i] - piv.v[i];
@@ -102,14 +106,43 @@ __global__ void __launch_bounds__(kPearsonThreads) pearson_nchw_kernel(const flo
 #pragma unroll
                 for (int j = 0; j < M; ++j) acc[2 + j][i] = fmaf(g, pcv[j], acc[2 + j][i]);
             }
+        };
+        if constexpr (VEC == 4) {
+            // register-free software pipeline: every thread keeps kDepth 16-byte cp.async copies in flight in its own
+            // shared-memory ring slots (128 B per thread, ~16 MB chip-wide: enough to cover HBM latency)
+            __shared__ float4 ring[kDepth][kPearsonThreads];
+            const int n_it = (k - ks + kSlices - 1) / kSlices;
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                if (d < n_it) cp_async_16(&ring[d][threadIdx.x], f + (int64_t)(ks + d * kSlices) * hw);
+                cp_async_commit_group();
+            }
+            for (int it = 0; it < n_it; ++it) {
+                cp_async_wait_group<kDepth - 1>();
+                const float4 q = ring[it % kDepth][threadIdx.x];
+                if (it + kDepth < n_it) cp_async_16(&ring[it % kDepth][threadIdx.x], f + (int64_t)(ks + (it + kDepth) * kSlices) * hw);
+                cp_async_commit_group();
+                PixVec<VEC> v;
+                v.v[0] = q.x; v.v[1] = q.y; v.v[2] = q.z; v.v[3] = q.w;
+                consume(v, ks + it * kSlices);
+            }
+            cp_async_wait_group<0>();
+        } else {
+#pragma unroll 4
+            for (int kk = ks; kk < k; kk += kSlices) {
+                PixVec<VEC> v;
+                v.load(f + (int64_t)kk * hw);
+                consume(v, kk);
+            }
         }
     }
-    // fold the 4 slices that share a warp (lanes l, l+8, l+16, l+24 hold the same pixels)
+    // fold the 8 slices that share a warp (lanes l, l+4, ..., l+28 hold the same pixels)
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float x = acc[a][i];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
             x += __shfl_xor_sync(0xffffffffu, x, 8);
             x += __shfl_xor_sync(0xffffffffu, x, 16);
             acc[a][i] = x;
@@ -178,18 +211,22 @@ __global__ void __launch_bounds__(256) pearson_rows_kernel(const float* __restri
 
 }  // namespace
 
-// ws layout: [pc m*k f32][stats 2*m f32]
-extern "C" int64_t uem_pearson_ws_bytes(int m, int k) { return ((int64_t)m * k + 2 * (int64_t)m + 4) * sizeof(float); }
+// ws layout: [pc max(m,8)*k f32 (row-major (m,k), or transposed (k,8) for the NCHW kernel)][stats 2*m f32]
+extern "C" int64_t uem_pearson_ws_bytes(int m, int k) {
+    const int64_t rows = m > kPcStride ? m : kPcStride;
+    return (rows * k + 2 * (int64_t)m + 4) * sizeof(float);
+}
 
 extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_t hw, const float* protos, int m, float eps,
                                          int reciprocal, float* out, void* ws, void* stream) {
     UEM_REQUIRE(feat && protos && out && ws && b > 0 && k > 0 && hw > 0, "uem_pearson_dist_nchw_f32: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     float* pc = (float*)ws;
-    float* stats = pc + (int64_t)m * k;
+    float* stats = pc + (int64_t)kPcStride * k;
     const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
+    UEM_CUDA(cudaMemsetAsync(pc, 0, (size_t)kPcStride * k * sizeof(float), st));  // unused class slots stay 0
     UEM_DISPATCH_C(m, {
-        proto_center_kernel<<<C, 256, 0, st>>>(protos, k, pc, stats);
+        proto_center_kernel<<<C, 256, 0, st>>>(protos, k, 1, pc, stats);
         if (vec) {
             dim3 grid(uem_div_up(hw, kPxLanes * 4), b);
             pearson_nchw_kernel<C, 4><<<grid, kPearsonThreads, 0, st>>>(feat, k, hw, pc, stats, eps, reciprocal, out);
@@ -207,8 +244,8 @@ extern "C" int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, c
     UEM_REQUIRE(feat1 && feat2 && out && ws && n > 0 && k > 0 && m > 0, "uem_pearson_dist_rows_f32: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     float* pc = (float*)ws;
-    float* stats = pc + (int64_t)m * k;
-    proto_center_kernel<<<m, 256, 0, st>>>(feat2, k, pc, stats);
+    float* stats = pc + (int64_t)(m > kPcStride ? m : kPcStride) * k;
+    proto_center_kernel<<<m, 256, 0, st>>>(feat2, k, 0, pc, stats);
     pearson_rows_kernel<<<uem_div_up(n, 8), 256, 0, st>>>(feat1, n, k, pc, stats, m, eps, out);
     UEM_CHECK_LAUNCH_N(2);
     return 0;

@@ -20,19 +20,25 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
                                                         int64_t* __restrict__ out, int32_t* __restrict__ status) {
     extern __shared__ unsigned bins[];  // [w][C+1]
     const int oy = blockIdx.x, bi = blockIdx.y;
-    for (int i = threadIdx.x; i < w * (C + 1); i += blockDim.x) bins[i] = 0;
+    // blockDim = (column pairs, kRowGroups): the s input rows of a block row are spread over threadIdx.y so that all
+    // of a thread's 128-bit loads are independent and issued together
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int i = tid; i < w * (C + 1); i += nthr) bins[i] = 0;
     __syncthreads();
     const int64_t* base = label + ((int64_t)bi * H + (int64_t)oy * s) * W;
-    const int usedW = w * s;  // trailing columns that do not fill a block are dropped (alignment.py:500)
+    // trailing columns that do not fill a block are dropped (alignment.py:500); gridDim.z CTAs share one output row
+    const int cells_per = (w + gridDim.z - 1) / gridDim.z;
+    const int cxs = blockIdx.z * cells_per, cxe = min(w, cxs + cells_per);
+    const int xs = cxs * s, xe = cxe * s;
     const int step = vec ? 2 : 1;
     int bad = 0;
-    for (int x0 = threadIdx.x * step; x0 < usedW; x0 += blockDim.x * step) {
+    for (int x0 = xs + threadIdx.x * step; x0 < xe; x0 += blockDim.x * step) {
         unsigned cnt0[C + 1], cnt1[C + 1];
 #pragma unroll
         for (int ci = 0; ci <= C; ++ci) { cnt0[ci] = 0; cnt1[ci] = 0; }
-        const bool two = vec && (x0 + 1 < usedW);
+        const bool two = vec && (x0 + 1 < xe);
 #pragma unroll 4
-        for (int r = 0; r < s; ++r) {
+        for (int r = threadIdx.y; r < s; r += blockDim.y) {
             int64_t a, b2 = ignore_label;
             if (vec) ldg_i64x2(base + (int64_t)r * W + x0, a, b2);
             else a = ldg_i64(base + (int64_t)r * W + x0);
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
     if (bad && status) atomicOr(status, 1);
     __syncthreads();
     const float area = (float)(s * s);
-    for (int cx = threadIdx.x; cx < w; cx += blockDim.x) {
+    for (int cx = cxs + tid; cx < cxe; cx += nthr) {
         const unsigned* bn = bins + cx * (C + 1);
         unsigned best = bn[0];
         int arg = 0;
@@ -71,7 +77,8 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
 }
 
 // ------------------------------------------------------------------------------- prototype sums
-constexpr int kAccThreads = 256;  // 8 warps = 8 channel rows per CTA
+constexpr int kAccThreads = 256;  // 8 warps
+constexpr int kChPerWarp = 4;     // channel rows per warp -> 32 channels per CTA
 
 // stage the class ids of image bi as bytes (255 = ignore / out of range)
 __device__ __forceinline__ void stage_labels(unsigned char* lab, const int64_t* __restrict__ label, int64_t hw, int c,
@@ -100,28 +107,148 @@ __global__ void __launch_bounds__(kAccThreads) proto_accum_kernel(const float* _
             if (lane == 0) cnt_partial[bi * C + ci] = n;
         }
     }
-    const int kk = blockIdx.x * (kAccThreads / 32) + warp;
-    if (kk >= k) return;
-    const float* f = feat + ((int64_t)bi * k + kk) * hw;
-    float acc[C];
+    // each warp streams kChPerWarp consecutive channel rows at once: kChPerWarp independent 128-bit loads in flight
+    // per thread and step, the byte label of a pixel is read once for all of them
+    const int kk0 = (blockIdx.x * (kAccThreads / 32) + warp) * kChPerWarp;
+    if (kk0 >= k) return;
+    const float* f = feat + ((int64_t)bi * k + kk0) * hw;
+    float acc[kChPerWarp][C];
 #pragma unroll
-    for (int ci = 0; ci < C; ++ci) acc[ci] = 0.f;
+    for (int q = 0; q < kChPerWarp; ++q)
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) acc[q][ci] = 0.f;
     const int64_t groups = hw / VEC;
-#pragma unroll 4
+#pragma unroll 2
     for (int64_t g = lane; g < groups; g += 32) {
-        PixVec<VEC> v;
-        v.load(f + g * VEC);
+        PixVec<VEC> v[kChPerWarp];
+#pragma unroll
+        for (int q = 0; q < kChPerWarp; ++q)
+            if (kk0 + q < k) v[q].load(f + (int64_t)q * hw + g * VEC);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const int l = lab[g * VEC + i];
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) acc[ci] += (l == ci) ? v.v[i] : 0.f;
+            for (int q = 0; q < kChPerWarp; ++q)
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) acc[q][ci] += (l == ci) ? v[q].v[i] : 0.f;
         }
     }
 #pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-        float x = warp_sum(acc[ci]);
-        if (lane == 0) partial[((int64_t)bi * C + ci) * k + kk] = x;
+    for (int q = 0; q < kChPerWarp; ++q) {
+        if (kk0 + q >= k) break;
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            float x = warp_sum(acc[q][ci]);
+            if (lane == 0) partial[((int64_t)bi * C + ci) * k + kk0 + q] = x;
+        }
+    }
+}
+
+// 128-bit path of the masked class sums, built for bytes in flight and few instructions:
+//   * the class ids of a pixel tile become C one-hot fp32 planes in shared memory (mask[c][px]);
+//   * every warp streams kChPerWarp channel rows through a per-thread cp.async ring (kRing steps x kChPerWarp
+//     x 16 B = 256 B in flight per thread, no staging registers);
+//   * sums use packed FFMA2 over pixel pairs: acc2[q][c] += (m.x,m.y)*(v.x,v.y) ; += (m.z,m.w)*(v.z,v.w)
+//     = 2 instructions per (channel, class, 4 pixels) instead of 12 compare/select/add.
+constexpr int kRing = 4;
+constexpr int kMaskTile = 2048;  // pixels per mask tile (C*8 KB of shared memory)
+
+template <int C>
+__global__ void __launch_bounds__(kAccThreads, 2) proto_accum_ring_kernel(const float* __restrict__ feat, int k, int64_t hw,
+                                                                          const int64_t* __restrict__ label, int64_t ignore_label,
+                                                                          int tile_px, float* __restrict__ partial,
+                                                                          int* __restrict__ cnt_partial) {
+    extern __shared__ __align__(16) unsigned char smem_acc[];
+    float* mask = reinterpret_cast<float*>(smem_acc);                                 // [C][tile_px]
+    float4* ring = reinterpret_cast<float4*>(mask + (size_t)C * tile_px);             // [kRing][kChPerWarp][kAccThreads]
+    const int bi = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk0 = (blockIdx.x * (kAccThreads / 32) + warp) * kChPerWarp;
+    const float* f = feat + ((int64_t)bi * k + kk0) * hw;
+    const int64_t* lab = label + (int64_t)bi * hw;
+
+    float2 acc2[kChPerWarp][C];
+#pragma unroll
+    for (int q = 0; q < kChPerWarp; ++q)
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) acc2[q][ci] = make_float2(0.f, 0.f);
+    int cnt[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) cnt[ci] = 0;
+
+    for (int64_t t0 = 0; t0 < hw; t0 += tile_px) {
+        const int tp = (int)min((int64_t)tile_px, hw - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tp; i += kAccThreads) {
+            const int64_t l = lab[t0 + i];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const bool hit = (l == ci) && (l != ignore_label);
+                mask[ci * tile_px + i] = hit ? 1.0f : 0.0f;
+                cnt[ci] += hit;
+            }
+        }
+        __syncthreads();
+        const int groups = tp / 4;
+        const int n_steps = (groups + 31) / 32;
+        auto issue = [&](int step) {
+            const int g = step * 32 + lane;
+            if (step < n_steps && g < groups) {
+#pragma unroll
+                for (int q = 0; q < kChPerWarp; ++q)
+                    if (kk0 + q < k)
+                        cp_async_16(&ring[((step % kRing) * kChPerWarp + q) * kAccThreads + threadIdx.x], f + (int64_t)q * hw + t0 + 4 * g);
+            }
+            cp_async_commit_group();
+        };
+#pragma unroll
+        for (int d = 0; d < kRing; ++d) issue(d);
+        for (int stp = 0; stp < n_steps; ++stp) {
+            cp_async_wait_group<kRing - 1>();
+            const int g = stp * 32 + lane;
+            if (g < groups) {
+                float4 m[C];
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) m[ci] = *reinterpret_cast<const float4*>(mask + ci * tile_px + 4 * g);
+#pragma unroll
+                for (int q = 0; q < kChPerWarp; ++q) {
+                    if (kk0 + q < k) {
+                        const float4 v = ring[((stp % kRing) * kChPerWarp + q) * kAccThreads + threadIdx.x];
+                        const float2 v01 = make_float2(v.x, v.y), v23 = make_float2(v.z, v.w);
+#pragma unroll
+                        for (int ci = 0; ci < C; ++ci) {
+                            acc2[q][ci] = __ffma2_rn(make_float2(m[ci].x, m[ci].y), v01, acc2[q][ci]);
+                            acc2[q][ci] = __ffma2_rn(make_float2(m[ci].z, m[ci].w), v23, acc2[q][ci]);
+                        }
+                    }
+                }
+            }
+            issue(stp + kRing);
+        }
+        cp_async_wait_group<0>();
+    }
+#pragma unroll
+    for (int q = 0; q < kChPerWarp; ++q) {
+        if (kk0 + q >= k) break;
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const float x = warp_sum(acc2[q][ci].x + acc2[q][ci].y);
+            if (lane == 0) partial[((int64_t)bi * C + ci) * k + kk0 + q] = x;
+        }
+    }
+    if (blockIdx.x == 0) {  // class counts of this image, once
+        __shared__ int scnt[kAccThreads / 32][C];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const int n = __reduce_add_sync(0xffffffffu, cnt[ci]);
+            if (lane == 0) scnt[warp][ci] = n;
+        }
+        __syncthreads();
+        if (threadIdx.x < C) {
+            int n = 0;
+            for (int i = 0; i < kAccThreads / 32; ++i) n += scnt[i][threadIdx.x];
+            cnt_partial[bi * C + threadIdx.x] = n;
+        }
     }
 }
 
@@ -217,13 +344,18 @@ extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W
     if (h == 0 || w == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int vec = (W % 2 == 0) && uem_aligned16(label) && (scale % 2 == 0);
-    const int cols = vec ? (w * scale + 1) / 2 : w * scale;
-    const int threads = min(512, max(32, ((cols + 31) / 32) * 32));
+    // enough CTAs for ~4 waves: split every output row into column segments of whole cells
+    int nseg = (int)min((int64_t)w, max((int64_t)1, (int64_t)(4 * UEM_SMS + (int64_t)h * b - 1) / ((int64_t)h * b)));
+    nseg = min(nseg, 64);
+    const int seg_cells = (w + nseg - 1) / nseg;
+    const int cols = vec ? (seg_cells * scale + 1) / 2 : seg_cells * scale;
+    const int threads = min(128, max(32, ((cols + 31) / 32) * 32));
+    const int row_groups = scale >= 8 ? 4 : (scale >= 4 ? 2 : 1);
     UEM_DISPATCH_C(n_classes, {
         size_t smem = (size_t)w * (C + 1) * sizeof(unsigned);
         UEM_REQUIRE(smem <= 48 * 1024, "uem_downscale_label_i64: output width %d too large", w);
-        dim3 grid(h, b);
-        downscale_kernel<C><<<grid, threads, smem, st>>>(label, H, W, scale, h, w, ignore_label, min_ratio, vec, out, status);
+        dim3 grid(h, b, nseg);
+        downscale_kernel<C><<<grid, dim3(threads, row_groups), smem, st>>>(label, H, W, scale, h, w, ignore_label, min_ratio, vec, out, status);
     });
     UEM_CHECK_LAUNCH();
     return 0;
@@ -247,10 +379,12 @@ extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t
     const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
     const size_t smem = (size_t)((hw + 15) / 16) * 16;
     UEM_DISPATCH_C(c, {
-        dim3 grid(uem_div_up(k, kAccThreads / 32), b);
+        dim3 grid(uem_div_up(k, (kAccThreads / 32) * kChPerWarp), b);
         if (vec) {
-            if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(proto_accum_kernel<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            proto_accum_kernel<C, 4><<<grid, kAccThreads, smem, st>>>(feat, k, hw, label, ignore_label, partial, cnt_partial);
+            const int tile_px = (int)min((int64_t)kMaskTile, ((hw + 3) / 4) * 4);
+            const size_t smem_r = (size_t)C * tile_px * 4 + (size_t)kRing * kChPerWarp * kAccThreads * 16;
+            UEM_CUDA(cudaFuncSetAttribute(proto_accum_ring_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            proto_accum_ring_kernel<C><<<grid, kAccThreads, smem_r, st>>>(feat, k, hw, label, ignore_label, tile_px, partial, cnt_partial);
         } else {
             if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(proto_accum_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             proto_accum_kernel<C, 1><<<grid, kAccThreads, smem, st>>>(feat, k, hw, label, ignore_label, partial, cnt_partial);

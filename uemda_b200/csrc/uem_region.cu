@@ -26,7 +26,16 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const int64_t* __restr
     int64_t mn = INT64_MAX, mx = INT64_MIN;
     const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
     if (vec) {
-        for (int64_t i = tid; i < n / 2; i += nth) {
+        const int64_t pairs = n / 2;
+        int64_t i = tid;
+        for (; i + 3 * nth < pairs; i += 4 * nth) {  // 4 independent 128-bit loads in flight per thread
+            int64_t a[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ldg_i64x2(x + 2 * (i + u * nth), a[2 * u], a[2 * u + 1]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { mn = min(mn, a[u]); mx = max(mx, a[u]); }
+        }
+        for (; i < pairs; i += nth) {
             int64_t a, b2;
             ldg_i64x2(x + 2 * i, a, b2);
             mn = min(mn, min(a, b2));
@@ -51,6 +60,41 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const int64_t* __restr
     }
 }
 
+// max only, accumulated with atomicMax into a slot the caller has zeroed (superpixel ids are >= 0): saves the
+// init launch on the fused chain
+__global__ void __launch_bounds__(kThreads) i64_max_kernel(const int64_t* __restrict__ x, int64_t n, int vec, int64_t* out) {
+    int64_t mx = 0;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (vec) {
+        const int64_t pairs = n / 2;
+        int64_t i = tid;
+        for (; i + 3 * nth < pairs; i += 4 * nth) {
+            int64_t a[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ldg_i64x2(x + 2 * (i + u * nth), a[2 * u], a[2 * u + 1]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mx = max(mx, a[u]);
+        }
+        for (; i < pairs; i += nth) {
+            int64_t a, b2;
+            ldg_i64x2(x + 2 * i, a, b2);
+            mx = max(mx, max(a, b2));
+        }
+        if (tid == 0 && (n & 1)) mx = max(mx, x[n - 1]);
+    } else {
+        for (int64_t i = tid; i < n; i += nth) mx = max(mx, x[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __shared__ int64_t smx[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; ++i) mx = max(mx, smx[i]);
+        if (mx > 0) atomicMax((long long*)out, (long long)mx);
+    }
+}
+
 // ---------------------------------------------------------------- f32 region reduce
 // table slot update
 template <int OP> __device__ __forceinline__ void slot_update_f32(unsigned* slot, float v);
@@ -71,7 +115,7 @@ template <> __device__ __forceinline__ float op_apply<UEM_REDUCE_SUM>(float a, f
 // table: (b,R,C) uint32 slots (MAX: ordered encoding, 0 = untouched; SUM: raw float bits, 0 = 0.0f)
 // cnt (optional, MEAN): (b,R) uint32 pixel counts
 template <int C, int VEC, int OP>
-__global__ void __launch_bounds__(kThreads) region_reduce_f32_kernel(const float* __restrict__ src, int64_t sb, int64_t sn,
+__global__ void __launch_bounds__(kThreads, 4) region_reduce_f32_kernel(const float* __restrict__ src, int64_t sb, int64_t sn,
                                                                      int64_t sc, const int64_t* __restrict__ index, int64_t N,
                                                                      int64_t R, const int64_t* __restrict__ hot_ptr, int64_t hot_val,
                                                                      int skip_hot, unsigned* __restrict__ table,
@@ -91,8 +135,21 @@ __global__ void __launch_bounds__(kThreads) region_reduce_f32_kernel(const float
 
     auto flush = [&]() {
         if (cur >= 0) {
+            unsigned* slot = tab + cur * C;
+            if (OP == UEM_REDUCE_MAX) {
+                // test-then-atomic: the C probes are independent L2 loads issued back to back
+                unsigned old[C];
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) slot_update_f32<OP>(tab + cur * C + ci, acc[ci]);
+                for (int ci = 0; ci < C; ++ci) old[ci] = ld_cg_u32(slot + ci);
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const unsigned e = f32_to_ordered(acc[ci]);
+                    if (e > old[ci]) atomicMax(slot + ci, e);
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) slot_update_f32<OP>(slot + ci, acc[ci]);
+            }
             if (cn) atomicAdd(cn + cur, cur_n);
         }
     };
@@ -323,11 +380,19 @@ __global__ void __launch_bounds__(kThreads) region_gather_label_kernel(const int
 
 }  // namespace
 
+int uem_i64_max_accumulate(const int64_t* x, int64_t n, int64_t* out_max, cudaStream_t st) {
+    UEM_REQUIRE(x && out_max && n > 0, "uem_i64_max_accumulate: bad arguments");
+    int grid = (int)min((int64_t)UEM_SMS * 8, (n / 8 + kThreads - 1) / kThreads + 1);
+    i64_max_kernel<<<grid, kThreads, 0, st>>>(x, n, uem_aligned16(x) ? 1 : 0, out_max);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int uem_i64_minmax(const int64_t* x, int64_t n, int64_t* out_min_max, void* stream) {
     UEM_REQUIRE(x && out_min_max && n > 0, "uem_i64_minmax: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     minmax_init_kernel<<<1, 1, 0, st>>>(out_min_max);
-    int grid = (int)min((int64_t)UEM_SMS * 4, (n / 2 + kThreads - 1) / kThreads + 1);
+    int grid = (int)min((int64_t)UEM_SMS * 8, (n / 8 + kThreads - 1) / kThreads + 1);
     minmax_kernel<<<grid, kThreads, 0, st>>>(x, n, uem_aligned16(x) ? 1 : 0, out_min_max);
     UEM_CHECK_LAUNCH_N(2);
     return 0;

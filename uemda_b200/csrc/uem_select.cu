@@ -135,42 +135,128 @@ __global__ void __launch_bounds__(kThreads) select_kernel(const float* __restric
                         out + (int64_t)bi * hw);
 }
 
-// same selection, class maxima folded from the per-CTA partials the refine kernel wrote
-template <int C, int VEC>
-__global__ void __launch_bounds__(kThreads) select_partials_kernel(const float* __restrict__ mask,
-                                                                   const float* __restrict__ part, int n_part, int64_t hw,
-                                                                   float top, float low, int64_t ignore_label,
-                                                                   int64_t* __restrict__ out) {
-    __shared__ float red[kThreads / 32][C];
-    __shared__ float thr[C];
-    const int bi = blockIdx.y;
-    float m[C];
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) m[ci] = -INFINITY;
-    for (int i = threadIdx.x; i < n_part; i += kThreads) {
-        const float* o = part + ((int64_t)bi * n_part + i) * (C + 1);  // [C maxima | min]
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) m[ci] = nanmax(m[ci], o[ci]);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) {
-        float v = warp_nanmax(m[ci]);
-        if (lane == 0) red[warp][ci] = v;
-    }
-    __syncthreads();
+// thresholds of image bi from the (b, C+2) stats table the refine kernel raised atomically:
+// [C ordered-encoded class maxima | ordered-encoded -(min) | bad flag]; an untouched slot (0) decodes to -inf and
+// the bad flag (a NaN/inf row sum was produced) poisons every threshold like torch.max does
+template <int C>
+__device__ __forceinline__ void thresholds_from_stats(const unsigned* __restrict__ stats, int bi, float top, float low, float* thr) {
     if (threadIdx.x < C) {
-        float v = red[0][threadIdx.x];
-        for (int i = 1; i < kThreads / 32; ++i) v = nanmax(v, red[i][threadIdx.x]);
+        const unsigned* s = stats + (int64_t)bi * (C + 2);
+        const unsigned e = s[threadIdx.x];
+        float v = e ? ordered_to_f32(e) : -INFINITY;
+        if (s[C + 1]) v = NAN;
         thr[threadIdx.x] = class_threshold(v, top, low);
     }
     __syncthreads();
+}
+
+// selection (+ optional entropy + UVEM weight) of the same map in one pass (the map is read once)
+template <int C, int VEC, bool EXTRA>
+__global__ void __launch_bounds__(kThreads) select_stats_kernel(const float* __restrict__ mask, const unsigned* __restrict__ stats,
+                                                                int64_t hw, float top, float low, int64_t ignore_label,
+                                                                int64_t* __restrict__ out, int has_uvem, float um, float ut,
+                                                                float uig, float ucl, float ucr, float* __restrict__ entropy,
+                                                                float* __restrict__ weight) {
+    __shared__ float thr[C];
+    const int bi = blockIdx.y;
+    thresholds_from_stats<C>(stats, bi, top, low, thr);
     const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (g * VEC >= hw) return;
-    select_body<C, VEC>(mask + (int64_t)bi * C * hw, thr, hw, g * VEC, ignore_label, 0, out + (int64_t)bi * hw);
+    const int64_t base = g * VEC;
+    const float* mk = mask + (int64_t)bi * C * hw;
+    if constexpr (!EXTRA) {
+        select_body<C, VEC>(mk, thr, hw, base, ignore_label, 0, out + (int64_t)bi * hw);
+    } else {
+        float p[C][VEC];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            PixVec<VEC> v;
+            v.load(mk + (int64_t)ci * hw + base);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) p[ci][i] = v.v[i];
+        }
+        int64_t lab[VEC];
+        PixVec<VEC> ev, wv;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            int wins = 0, first = 0;
+            float px[C];
+#pragma unroll
+            for (int ci = C - 1; ci >= 0; --ci) {
+                px[ci] = p[ci][i];
+                const bool w = px[ci] > thr[ci];
+                wins += w;
+                first = w ? ci : first;
+            }
+            lab[i] = (wins == 1) ? (int64_t)first : ignore_label;
+            const float u = entropy_px<C>(px);
+            ev.v[i] = u;
+            wv.v[i] = has_uvem ? uvem_weight_dev(u, um, ut, uig, ucl, ucr) : 1.0f;
+        }
+        store_ids<VEC>(out + (int64_t)bi * hw + base, lab);
+        if (entropy) ev.store(entropy + (int64_t)bi * hw + base);
+        if (weight) wv.store(weight + (int64_t)bi * hw + base);
+    }
+}
+
+// decode the stats table into plain floats: cmax/cmin (b*c... cmin is per image) for the host-side range assert
+__global__ void class_stats_decode_kernel(const unsigned* __restrict__ stats, int b, int c, float* __restrict__ cmax,
+                                          float* __restrict__ imin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * (c + 1)) return;
+    const int bi = i / (c + 1), j = i - bi * (c + 1);
+    const unsigned* s = stats + (int64_t)bi * (c + 2);
+    const bool bad = s[c + 1] != 0;
+    const unsigned e = s[j];
+    float v = e ? ordered_to_f32(e) : -INFINITY;
+    if (j == c) v = -v;
+    if (bad) v = NAN;
+    if (j < c) cmax[bi * c + j] = v; else imin[bi] = v;
 }
 
 }  // namespace
+
+extern "C" int uem_select_entropy_stats_f32(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw,
+                                            float cutoff_top, float cutoff_low, int64_t ignore_label, int64_t* out,
+                                            const float* uvem, float* entropy, float* weight, void* stream) {
+    UEM_REQUIRE(mask && class_stats && out && b > 0 && hw > 0, "uem_select_entropy_stats_f32: bad arguments");
+    UEM_REQUIRE(!(weight && !uvem), "uem_select_entropy_stats_f32: weight output needs the uvem parameter block");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = uem_aligned16(mask) && uem_aligned16(out) && (hw % 4 == 0) && (!entropy || uem_aligned16(entropy)) &&
+                     (!weight || uem_aligned16(weight));
+    const int hu = uvem ? 1 : 0;
+    const float um = hu ? uvem[0] : 0.f, ut = hu ? uvem[1] : 1.f, uig = hu ? uvem[2] : 1.f, ucl = hu ? uvem[3] : 0.f,
+                ucr = hu ? uvem[4] : 0.f;
+    const bool extra = entropy || weight;
+    UEM_DISPATCH_C(c, {
+        if (vec) {
+            dim3 grid(uem_div_up(hw / 4, kThreads), b);
+            if (extra)
+                select_stats_kernel<C, 4, true><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
+                                                                           out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+            else
+                select_stats_kernel<C, 4, false><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
+                                                                            out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+        } else {
+            dim3 grid(uem_div_up(hw, kThreads), b);
+            if (extra)
+                select_stats_kernel<C, 1, true><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
+                                                                           out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+            else
+                select_stats_kernel<C, 1, false><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
+                                                                            out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+        }
+    });
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_class_stats_decode_f32(const uint32_t* class_stats, int b, int c, float* cmax, float* image_min, void* stream) {
+    UEM_REQUIRE(class_stats && cmax && image_min && b > 0 && c > 0, "uem_class_stats_decode_f32: bad arguments");
+    class_stats_decode_kernel<<<uem_div_up((int64_t)b * (c + 1), 128), 128, 0, (cudaStream_t)stream>>>(class_stats, b, c, cmax, image_min);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int64_t uem_class_max_ws_bytes(int b, int c, int64_t hw) {
     return (int64_t)b * c * class_max_splits(b, c, hw) * 3 * sizeof(float);
@@ -204,28 +290,6 @@ extern "C" int uem_pseudo_select_f32(const float* mask, const float* cmax, int b
         } else {
             dim3 grid(uem_div_up(hw, kThreads), b);
             select_kernel<C, 1><<<grid, kThreads, 0, st>>>(mask, cmax, hw, cutoff_top, cutoff_low, ignore_label, variant, out);
-        }
-    });
-    UEM_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int uem_pseudo_select_partials_f32(const float* mask, const float* class_max_partial, int n_partials, int b,
-                                              int c, int64_t hw, float cutoff_top, float cutoff_low,
-                                              int64_t ignore_label, int64_t* out, void* stream) {
-    UEM_REQUIRE(mask && class_max_partial && out && n_partials > 0 && b > 0 && hw > 0,
-                "uem_pseudo_select_partials_f32: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = uem_aligned16(mask) && uem_aligned16(out) && (hw % 4 == 0);
-    UEM_DISPATCH_C(c, {
-        if (vec) {
-            dim3 grid(uem_div_up(hw / 4, kThreads), b);
-            select_partials_kernel<C, 4><<<grid, kThreads, 0, st>>>(mask, class_max_partial, n_partials, hw, cutoff_top,
-                                                                    cutoff_low, ignore_label, out);
-        } else {
-            dim3 grid(uem_div_up(hw, kThreads), b);
-            select_partials_kernel<C, 1><<<grid, kThreads, 0, st>>>(mask, class_max_partial, n_partials, hw, cutoff_top,
-                                                                    cutoff_low, ignore_label, out);
         }
     });
     UEM_CHECK_LAUNCH();

@@ -9,14 +9,15 @@ __all__ = ["pseudo_selection", "pseudo_selection1"]
 
 def _class_max_checked(mask):
     """per-(b,c) max of `mask`; reproduces the reference's range assert (pseudo_generation.py:36,71)."""
-    cached = getattr(mask, "_uem_partials", None)
+    cached = getattr(mask, "_uem_stats", None)
     if cached is not None and cached[1] == mask._version and cached[0].shape[0] == mask.shape[0]:
-        partial = cached[0]                      # (b, n_part, c+1) written by the refine kernel
+        stats = cached[0]                        # (b, c+2) statistics table raised by the refine kernel
         if config.strict_asserts:
-            host = partial.cpu()
-            hi, lo = host[..., :-1].max().item(), host[..., -1].min().item()
+            cmax, imin = ops.class_stats_decode(stats, mask.shape[1])
+            host = torch.cat([cmax.reshape(-1), imin]).cpu()
+            hi, lo = host[:cmax.numel()].max().item(), host[cmax.numel():].min().item()
             assert hi <= 1 and lo >= 0, print(hi, lo)
-        return None, partial
+        return None, stats
     cmax, cmin, _ = ops.class_max(mask)
     if config.strict_asserts:
         host = torch.stack([cmax, cmin]).cpu()
@@ -28,9 +29,9 @@ def _class_max_checked(mask):
 def _select(mask, cutoff_top, cutoff_low, return_type, ignore_label, variant):
     assert return_type in ["ndarray", "tensor"]
     assert mask.dim() == 4, "mask must be (b, c, h, w)"
-    cmax, partial = _class_max_checked(mask)
-    if partial is not None and variant == 0:
-        ret = ops.pseudo_select_partials(mask, partial, cutoff_top, cutoff_low, ignore_label)
+    cmax, stats = _class_max_checked(mask)
+    if stats is not None and variant == 0:
+        ret = ops.pseudo_select_stats(mask, stats, cutoff_top, cutoff_low, ignore_label)
     else:
         if cmax is None:
             cmax = ops.class_max(mask)[0]

@@ -2,7 +2,7 @@
 
 ``refine_select`` is one C-ABI call (uem_mine_refine_select_f32) that enqueues, with no host sync,
     [batch max superpixel id] -> [region max of soft] -> [Pearson 1/dist at feature res] ->
-    [fused full-res refine (+ per-class max partials)] -> [pseudo-label selection]
+    [fused full-res refine (+ per-class max statistics)] -> [pseudo-label selection]
 which is tools/train_ssl_uem.py:209-214 / vis_corrected_pseudo_labels.py:185-189 of the reference.
 
 ``ShardedMiner`` shards the target batch (or tile list) over the ranks of a torch.distributed job
@@ -12,6 +12,8 @@ which is tools/train_ssl_uem.py:209-214 / vis_corrected_pseudo_labels.py:185-189
   * class histogram (c+1) (balance.py:49-52)                         -> all_reduce(SUM), 64 B
 cross the NVLink fabric.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -19,10 +21,12 @@ from . import ops
 
 
 def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pred2=None, sup=None, num_regions=None,
-                  ignored_id=None, eps=1e-7, select=None, ws=None):
-    """Returns (refined (b,c,H,W) fp32, hard (b,H,W) int64 or None).
+                  ignored_id=None, eps=1e-7, select=None, ws=None, uvem=None, want_entropy=False):
+    """Returns (refined (b,c,H,W) fp32, hard (b,H,W) int64 or None); with ``uvem``/``want_entropy`` the tuple
+    grows to (refined, hard, entropy (b*H*W,) or None, uvem_weight (b*H*W,) or None), all from the same pass.
 
     select: None or (cutoff_top, cutoff_low, ignore_label).
+    uvem: None or (m, threshold, gamma) of UVEMLoss (balance.py:345-423); needs ``select``.
     num_regions: capacity R of the region table (ids must lie in [0,R)); None -> read sup.max() back
         (one 8-byte device->host copy, like torch_scatter's ``int(index.max())+1``).
     ignored_id: optional (1,) int64 device tensor holding the batch-global max id (e.g. after an
@@ -65,16 +69,23 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
     if select is not None:
         top, low, ign = select
         hard = torch.empty((b, H, W), dtype=torch.int64, device=soft.device)
+    ent = wgt = uv = None
+    if want_entropy or uvem is not None:
+        assert select is not None, "entropy / UVEM weight are produced by the selection pass"
+        ent = torch.empty(b * H * W, dtype=torch.float32, device=soft.device)
+        if uvem is not None:
+            wgt = torch.empty(b * H * W, dtype=torch.float32, device=soft.device)
+            uv = (ctypes.c_float * 5)(*ops._uvem_coefs(*uvem))
     L.check(lib.uem_mine_refine_select_f32(
         int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
-        L.ptr(hard), L.ptr(ws), L.stream_of(soft)))
-    # per-CTA [class maxima | min] of `refined`, reused by pseudo_selection() so it needs no second max pass
-    nparts = lib.uem_label_refine_partials(H)
-    off = need - ((b * nparts * (c + 1) * 4 + 15) // 16) * 16
-    partial = ws[off:off + b * nparts * (c + 1) * 4].view(torch.float32).view(b, nparts, c + 1)
-    refined._uem_partials = (partial, refined._version)
-    refined._uem_ws = ws
+        L.ptr(hard), uv, L.ptr(ent), L.ptr(wgt), L.ptr(ws), L.stream_of(soft)))
+    # [class maxima | -min | bad] of `refined`, reused by pseudo_selection() so it needs no second max pass
+    off = lib.uem_mine_ws_stats_offset(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
+    stats = ws[off:off + b * (c + 2) * 4].view(torch.int32).view(b, c + 2).clone()
+    refined._uem_stats = (stats, refined._version)
+    if want_entropy or uvem is not None:
+        return refined, hard, ent, wgt
     return refined, hard
 
 

@@ -125,15 +125,34 @@ def pseudo_select(mask, cmax, cutoff_top, cutoff_low, ignore_label=-1, variant=0
     return out
 
 
-def pseudo_select_partials(mask, partial, cutoff_top, cutoff_low, ignore_label=-1):
-    L.require_cuda(mask, partial)
+def pseudo_select_stats(mask, stats, cutoff_top, cutoff_low, ignore_label=-1, uvem=None, want_entropy=False):
+    """pseudo_selection fed by the (b, c+2) uint32 class-statistics table the refine kernel raised; with
+    ``uvem=(m, t, gamma)`` / ``want_entropy`` also the entropy and UVEM weight of the same pass.
+    Returns hard, or (hard, entropy|None, weight|None)."""
+    import ctypes
+    L.require_cuda(mask, stats)
     mask = L.f32c(mask.detach())
     b, c, h, w = mask.shape
     lib = L.bind(mask)
     out = torch.empty((b, h, w), dtype=torch.int64, device=mask.device)
-    L.check(lib.uem_pseudo_select_partials_f32(L.ptr(mask), L.ptr(partial), partial.shape[1], b, c, h * w, f32(cutoff_top),
-                                               f32(cutoff_low), int(ignore_label), L.ptr(out), L.stream_of(mask)))
-    return out
+    extra = want_entropy or uvem is not None
+    ent = torch.empty(b * h * w, dtype=torch.float32, device=mask.device) if extra else None
+    wgt = torch.empty(b * h * w, dtype=torch.float32, device=mask.device) if uvem is not None else None
+    uv = (ctypes.c_float * 5)(*_uvem_coefs(*uvem)) if uvem is not None else None
+    L.check(lib.uem_select_entropy_stats_f32(L.ptr(mask), L.ptr(stats), b, c, h * w, f32(cutoff_top), f32(cutoff_low),
+                                             int(ignore_label), L.ptr(out), uv, L.ptr(ent), L.ptr(wgt), L.stream_of(mask)))
+    return (out, ent, wgt) if extra else out
+
+
+def class_stats_decode(stats, c):
+    """(b, c+2) uint32 statistics table -> cmax (b,c) fp32, image_min (b,) fp32 (NaN where the bad flag is set)."""
+    L.require_cuda(stats)
+    b = stats.shape[0]
+    lib = L.bind(stats)
+    cmax = torch.empty((b, c), dtype=torch.float32, device=stats.device)
+    imin = torch.empty((b,), dtype=torch.float32, device=stats.device)
+    L.check(lib.uem_class_stats_decode_f32(L.ptr(stats), b, c, L.ptr(cmax), L.ptr(imin), L.stream_of(stats)))
+    return cmax, imin
 
 
 # --------------------------------------------------------------------------------------------- seam
@@ -255,8 +274,8 @@ def pearson_dist_rows(feat1, feat2, eps=1e-7):
 
 # --------------------------------------------------------------------------------------------- a6
 def label_refine(views, soft, temp, simi=None, pred1=None, pred2=None, sup=None, region_max=None, ignored_id=None,
-                 want_partials=True):
-    """One fused full-resolution kernel (alignment.py:215-292).  Returns (refined, partials|None)."""
+                 want_stats=True):
+    """One fused full-resolution kernel (alignment.py:215-292).  Returns (refined, class stats table|None)."""
     L.require_cuda(soft, simi, pred1, pred2, sup, region_max, ignored_id)
     soft = L.f32c(soft.detach())
     b, c, H, W = soft.shape
@@ -265,13 +284,12 @@ def label_refine(views, soft, temp, simi=None, pred1=None, pred2=None, sup=None,
     h, w = (low.shape[-2], low.shape[-1]) if low is not None else (0, 0)
     R = region_max.shape[1] if region_max is not None else 0
     out = torch.empty_like(soft)
-    partial = None
-    if want_partials:
-        partial = torch.empty((b, lib.uem_label_refine_partials(H), c + 1), dtype=torch.float32, device=soft.device)
+    stats = torch.zeros((b, c + 2), dtype=torch.int32, device=soft.device) if want_stats else None
+    ws = L.workspace(lib.uem_label_refine_ws_bytes(b, c, R), soft)
     L.check(lib.uem_label_refine_f32(int(views), L.ptr(simi), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), L.ptr(region_max),
-                                     R, L.ptr(ignored_id), L.ptr(soft), b, c, H, W, f32(temp), L.ptr(out), L.ptr(partial),
-                                     L.stream_of(soft)))
-    return out, partial
+                                     R, L.ptr(ignored_id), L.ptr(soft), b, c, H, W, f32(temp), L.ptr(out), L.ptr(stats),
+                                     L.ptr(ws), L.stream_of(soft)))
+    return out, stats
 
 
 def proto_weight_4pixel(simi, hard, ignore_label=-1, eps=1e-7):
