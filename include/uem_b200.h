@@ -156,8 +156,9 @@ UEM_API int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, cons
  * alignment.py:241) (SUP view).  soft (b,c,H,W) -> out (b,c,H,W).
  * class_stats (optional, may be NULL): the (b, c+2) statistics table of `out` described above, zeroed by the
  * caller, consumed by uem_select_entropy_stats_f32.
- * ws: uem_label_refine_ws_bytes(b,c,R) bytes (per-region weights of the SUP view; may be NULL without it). */
-UEM_API int64_t uem_label_refine_ws_bytes(int b, int c, int64_t R);
+ * ws: uem_label_refine_ws_bytes(b,c,R,W) bytes (per-region weights of the SUP view + column tables; may be NULL
+ * without that view). */
+UEM_API int64_t uem_label_refine_ws_bytes(int b, int c, int64_t R, int W);
 UEM_API int uem_label_refine_f32(int views, const float* simi, const float* pred1, const float* pred2, int h,
                          int w, const int64_t* sup, const float* region_max, int64_t R,
                          const int64_t* ignored_id, const float* soft, int b, int c, int H, int W,

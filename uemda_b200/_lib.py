@@ -10,7 +10,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuem_b200.so")
+# UEM_B200_LIB: development override (A/B builds of the same ABI); the product default is the in-tree library
+LIB_PATH = os.environ.get("UEM_B200_LIB") or os.path.join(_HERE, "libuem_b200.so")
 
 _c = ctypes
 _P = _c.c_void_p
@@ -42,7 +43,7 @@ SIGNATURES = {
     "uem_pearson_ws_bytes": (_L, [_I, _I]),
     "uem_pearson_dist_nchw_f32": (_I, [_P, _I, _I, _L, _P, _I, _F, _I, _P, _P, _P]),
     "uem_pearson_dist_rows_f32": (_I, [_P, _L, _I, _P, _I, _F, _P, _P, _P]),
-    "uem_label_refine_ws_bytes": (_L, [_I, _I, _L]),
+    "uem_label_refine_ws_bytes": (_L, [_I, _I, _L, _I]),
     "uem_label_refine_f32": (_I, [_I, _P, _P, _P, _I, _I, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "uem_class_stats_bytes": (_L, [_I, _I]),
     "uem_select_entropy_stats_f32": (_I, [_P, _P, _I, _I, _L, _F, _F, _L, _P, _P, _P, _P, _P]),

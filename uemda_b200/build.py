@@ -37,8 +37,11 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib=None, obj_dir=None):
+    """extra_flags / lib / obj_dir: development A/B builds (e.g. -DUEM_... knobs) into a separate library."""
     nvcc = _nvcc()
+    LIB = lib or globals()["LIB"]
+    OBJ = obj_dir or globals()["OBJ"]
     os.makedirs(OBJ, exist_ok=True)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
@@ -48,7 +51,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -73,5 +76,11 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")), None)
+    if tag:
+        path = build(force=True, verbose="--verbose" in sys.argv, extra_flags=flags,
+                     lib=os.path.join(HERE, "libuem_b200_%s.so" % tag), obj_dir=os.path.join(CSRC, ".obj_" + tag))
+    else:
+        path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, extra_flags=flags)
     print(path)

@@ -24,11 +24,35 @@
 //   * per-(image,class) maxima for pseudo_selection (pseudo_generation.py:76) fall out as a (b, c+2) stats
 //     table updated with one atomicMax per class per CTA.
 #include "uem_common.cuh"
+#include "uem_tma.cuh"
 
 int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, const int64_t* index, int b, int64_t N,
                          int c, int64_t R, int op, const int64_t* hot_ptr, int64_t hot_val, int skip_hot, unsigned* table,
                          unsigned* cnt, int* status, cudaStream_t st);
 int uem_i64_max_accumulate(const int64_t* x, int64_t n, int64_t* out_max, cudaStream_t st);
+
+#ifndef UEM_REFINE_MINB
+#define UEM_REFINE_MINB 4   // resident 128-thread CTAs per SM the TMA kernel is compiled for (register cap = 64K/(128*MINB))
+#endif
+#ifndef UEM_REFINE_EXP
+#define UEM_REFINE_EXP 0    // development experiments: 1 = no soft/id loads (compute floor), 2 = no view math (memory floor)
+#endif
+#ifndef UEM_XTAB_GLOBAL
+#define UEM_XTAB_GLOBAL 0   // 1: horizontal-weight table read from global (L1) instead of a per-CTA shared copy
+#endif
+
+#ifndef UEM_NO_PACKED
+#define UEM_NO_PACKED 0     // development experiment: 1 = scalar FFMA/FMUL/FADD instead of the packed fp32x2 forms
+#endif
+#if UEM_NO_PACKED
+#define UEM_FFMA2(a, b, c) make_float2(fmaf((a).x, (b).x, (c).x), fmaf((a).y, (b).y, (c).y))
+#define UEM_FMUL2(a, b) make_float2((a).x * (b).x, (a).y * (b).y)
+#define UEM_FADD2(a, b) make_float2((a).x + (b).x, (a).y + (b).y)
+#else
+#define UEM_FFMA2(a, b, c) __ffma2_rn(a, b, c)
+#define UEM_FMUL2(a, b) __fmul2_rn(a, b)
+#define UEM_FADD2(a, b) __fadd2_rn(a, b)
+#endif
 
 namespace {
 
@@ -46,9 +70,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef UEM_NO_MUFU
+    return fmaf(x, x, 1.0f);  // development experiment only: takes the XU pipe out of the picture
+#else
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -69,7 +97,8 @@ struct RefineParams {
     float temp;
     int div_temp;           // temp is not a power of two: the staged logits are divided (one rounding) instead
     const int64_t* sup;
-    const float* sw;        // (b,R,CP) per-region superpixel-view weights
+    const float* sw;        // (b,R+1,CP) per-region superpixel-view weights
+    const float4* xtab;     // (W/4, 4) horizontal 3-tap weights per 4-pixel group (TMA kernel)
     int64_t R;
     const int64_t* ignored_id;
     const float* soft;
@@ -103,6 +132,22 @@ template <int PC> __device__ __forceinline__ float exp_shifted2(float2 (&z)[PC])
         const float2 d = __fmul2_rn(__fadd2_rn(z[j], nmx), l2e);
         z[j] = make_float2(ex2_approx(d.x), ex2_approx(d.y));
         acc = __fadd2_rn(acc, z[j]);
+    }
+    return acc.x + acc.y;
+}
+
+// same, inputs already in the log2 domain (taps pre-scaled by log2 e): e_c = 2^(z_c - max z)
+template <int PC> __device__ __forceinline__ float exp2_shifted2(float2 (&z)[PC]) {
+    float mx = fmaxf(z[0].x, z[0].y);
+#pragma unroll
+    for (int j = 1; j < PC; ++j) mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
+    const float2 nmx = make_float2(-mx, -mx);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < PC; ++j) {
+        const float2 d = UEM_FADD2(z[j], nmx);
+        z[j] = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+        acc = UEM_FADD2(acc, z[j]);
     }
     return acc.x + acc.y;
 }
@@ -185,9 +230,9 @@ __device__ __forceinline__ void flush_stats(unsigned* stats, int bi, float (&cma
     bad = false;
 }
 
-// FAST: all three views, two heads, 128-bit path, >=3x up-sampling (branch-free packed 3-tap form).
-// Otherwise: any view subset / one head / scalar path / any scale (2-tap scalar form, runtime view flags).
-template <int C, int VEC, bool FAST>
+// Generic form: any view subset / one head / scalar path / any scale (2-tap scalar math, runtime view flags).
+// The default configuration (all views, two heads, 128-bit rows, >=3x up-sampling) runs refine_tma_kernel below.
+template <int C, int VEC>
 __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineParams p) {
     constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE, PC = Lay<C>::PC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -220,7 +265,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
         }
         const float* softb = p.soft + (int64_t)bi * C * HW;
         float* outb = p.out + (int64_t)bi * C * HW;
-        const float* swb = p.sw + (int64_t)bi * p.R * CP;
+        const float* swb = p.sw + (int64_t)bi * (p.R + 1) * CP;  // row R of every image: the all-ones sentinel
         for (int g0 = 0; g0 < groups; g0 += kRefineThreads) {
             const int g = g0 + threadIdx.x;
             const bool active = g < groups;
@@ -250,85 +295,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
             if (!active) { cp_async_wait_group<0>(); continue; }
 
             float wgt[C][VEC];
-            if constexpr (FAST) {
-                // horizontal taps: column a = i0 of the first pixel; pixel i uses columns a+d_i, a+d_i+1 with the
-                // 3-tap weights (l0,l1,0) or (0,l0,l1): same products, same rounding as the 2-tap form
-                float wa[VEC], wb[VEC], wc[VEC];
-                const int a = make_lerp(x0, p.w, p.sx).i0;
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const Lerp lx = make_lerp(x0 + i, p.w, p.sx);
-                    const bool d = lx.i0 != a;
-                    wa[i] = d ? 0.f : lx.l0;
-                    wb[i] = d ? lx.l0 : lx.l1;
-                    wc[i] = d ? lx.l1 : 0.f;
-                }
-                const float* col = row + a * STRIDE;
-                float2 wgt2[PC][VEC];
-                {   // prototype view
-                    float2 t[3][PC];
-                    load_tap3p<C>(col, STRIDE, t);
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
-                        float2 z[PC];
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) z[j] = __ffma2_rn(c2, t[2][j], __ffma2_rn(b2, t[1][j], __fmul2_rn(a2, t[0][j])));
-                        const float S = exp_shifted2<PC>(z);
-                        const float rs = fmaf(-1e-7f, S, 1.0f);
-                        const float2 rs2 = make_float2(rs, rs);
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) wgt2[j][i] = __fmul2_rn(z[j], rs2);
-                    }
-                }
-                {   // prediction view, two heads
-                    float2 t[3][PC], u[3][PC];
-                    load_tap3p<C>(col + CP, STRIDE, t);
-                    load_tap3p<C>(col + 2 * CP, STRIDE, u);
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
-                        float2 z[PC], z2[PC];
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) {
-                            z[j] = __ffma2_rn(c2, t[2][j], __ffma2_rn(b2, t[1][j], __fmul2_rn(a2, t[0][j])));
-                            z2[j] = __ffma2_rn(c2, u[2][j], __ffma2_rn(b2, u[1][j], __fmul2_rn(a2, u[0][j])));
-                        }
-                        const float S1 = exp_shifted2<PC>(z);
-                        const float S2 = exp_shifted2<PC>(z2);
-                        const float h1 = 0.5f * rcp_approx(S1), h2 = 0.5f * rcp_approx(S2);
-                        const float2 h1v = make_float2(h1, h1), h2v = make_float2(h2, h2);
-                        float mx = 0.f;
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) {
-                            z[j] = __ffma2_rn(z[j], h1v, __fmul2_rn(z2[j], h2v));
-                            mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
-                        }
-                        const float inv = rcp_approx(mx + 1e-7f);
-                        const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) wgt2[j][i] = __ffma2_rn(z[j], inv2, wgt2[j][i]);
-                    }
-                }
-                cp_async_wait_group<0>();
-                // superpixel view: multiplicative outside the ignored id
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const int64_t rid = ids_s[(size_t)threadIdx.x * VEC + i];
-                    if (rid != ignored_id && (uint64_t)rid < (uint64_t)p.R) {
-#pragma unroll
-                        for (int q = 0; q < CP / 4; ++q) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(swb + rid * CP) + q);
-                            wgt2[2 * q][i] = __fmul2_rn(wgt2[2 * q][i], make_float2(v.x, v.y));
-                            if (2 * q + 1 < PC) wgt2[2 * q + 1][i] = __fmul2_rn(wgt2[2 * q + 1][i], make_float2(v.z, v.w));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int ci = 0; ci < C; ++ci)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) wgt[ci][i] = (ci & 1) ? wgt2[ci >> 1][i].y : wgt2[ci >> 1][i].x;
-            } else {
+            {
                 bool have = false;
                 if (vP) {  // prototype view: softmax(T=1) of the up-sampled 1/distance, peak-normalised
 #pragma unroll
@@ -441,13 +408,339 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
     if (cur_b >= 0 && p.stats) flush_stats<C>(p.stats, cur_b, cmax, cmin, bad, red);
 }
 
-// superpixel-view weight of every (image, region): softmax(region_max/temp) / (max + 1e-7)  (alignment.py:252-253)
-// table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R,CP)
+// ------------------------------------------------------------------------------------------------
+// Default configuration (all three views, two heads, W % 4 == 0, >= 3x up-sampling): TMA-fed persistent kernel.
+//   * one CTA = 128 threads = one contiguous range of image rows; a thread = 4 consecutive pixels;
+//   * the soft rows (C class planes) and the superpixel-id row of a whole image row are brought in by the TMA
+//     engine: C+1 cp.async.bulk copies issued by one thread, completion on an mbarrier, NSTAGE rows in flight per
+//     CTA (no per-thread address math, no staging registers, 16 KB per row in flight at config 2);
+//   * the low-res maps (1/dist, two logit heads) of the NEXT row are fetched with 4-byte cp.async into a raw buffer
+//     while the current row is computed, then interpolated vertically into a double-buffered tap row
+//     (pre-scaled by log2(e) [/temp] so the softmax exponent is a bare EX2): one __syncthreads per row;
+//   * horizontal interpolation weights (3-tap form: same products and roundings as PyTorch's 2-tap lerp) depend
+//     on the column only and are tabulated once per CTA;
+//   * class pairs share packed fp32x2 instructions (FFMA2/FMUL2/FADD2);
+//   * the superpixel view is a branch-free gather of 2 x LDG.128 from the per-region weight table (ignored /
+//     out-of-range ids redirect to an all-ones sentinel row).
+// ------------------------------------------------------------------------------------------------
+// horizontal 3-tap weights of 4-pixel group g: column a = i0 of the first pixel; pixel i uses (a, a+1) with weights
+// (l0, l1, 0) or (a+1, a+2) with (0, l0, l1): the same products and roundings as PyTorch's 2-tap lerp
 template <int C>
-__global__ void __launch_bounds__(256) region_weight_kernel(const void* __restrict__ table, int encoded, int64_t regions, float temp,
-                                                            float inv_temp, int div_temp, float* __restrict__ sw) {
+__device__ __forceinline__ void xtab_entry(float4* e, int g, int w, float sx) {
+    const int x0 = g * 4;
+    const int a = make_lerp(x0, w, sx).i0;
+    float wa[4], wb[4], wc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const Lerp lx = make_lerp(x0 + i, w, sx);
+        const bool d = lx.i0 != a;
+        wa[i] = d ? 0.f : lx.l0;
+        wb[i] = d ? lx.l0 : lx.l1;
+        wc[i] = d ? lx.l1 : 0.f;
+    }
+    e[0] = make_float4(__int_as_float(a * Lay<C>::STRIDE), 0.f, 0.f, 0.f);
+    e[1] = make_float4(wa[0], wa[1], wa[2], wa[3]);
+    e[2] = make_float4(wb[0], wb[1], wb[2], wb[3]);
+    e[3] = make_float4(wc[0], wc[1], wc[2], wc[3]);
+}
+
+struct TmaLayout {
+    uint32_t stage_bytes, off_row, off_xt, off_raw, off_bar, total;
+};
+__host__ __device__ inline TmaLayout tma_layout(int C, int W, int w, int nstage) {
+    const int CP = (C + 3) & ~3;
+    TmaLayout L;
+    L.stage_bytes = (uint32_t)W * (4u * C + 8u);
+    uint32_t n = (uint32_t)nstage * L.stage_bytes;
+    L.off_row = n; n += 2u * (uint32_t)(w + 2) * 3u * CP * 4u;
+    L.off_xt = n; n += UEM_XTAB_GLOBAL ? 0u : (uint32_t)(W / 4) * 64u;
+    L.off_raw = n; n += ((2u * 3u * C * (uint32_t)w * 4u) + 15u) & ~15u;
+    L.off_bar = n; n += 8u * (((uint32_t)nstage + 2u) & ~1u);  // full[nstage] + the raw-row barrier
+    L.total = n;
+    return L;
+}
+
+template <int C, int NSTAGE, int NT>
+__global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_kernel(const RefineParams p) {
+    constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE, PC = Lay<C>::PC, NW = NT / 32;
+    constexpr float kL2E = 1.4426950408889634f;
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    unsigned char* const smem_raw = smem_tma;
+    __shared__ float red[NW][C + 2];
+    const int W = p.W, w = p.w, H = p.H, groups = W >> 2;
+    const TmaLayout L = tma_layout(C, W, w, NSTAGE);
+    float* rowbuf = reinterpret_cast<float*>(smem_raw + L.off_row);   // [2][w+2][STRIDE]
+#if UEM_XTAB_GLOBAL
+    const float4* __restrict__ xtab = p.xtab;
+#else
+    float4* xtab = reinterpret_cast<float4*>(smem_raw + L.off_xt);    // [groups][4]: {a, -, -, -}, wa[4], wb[4], wc[4]
+#endif
+    float* raw = reinterpret_cast<float*>(smem_raw + L.off_raw);      // [2][3C][w]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    const int rowlen = (w + 2) * STRIDE;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t HW = (int64_t)H * W;
+    const int hw_low = p.h * w;
+
+    const int64_t total_rows = (int64_t)p.b * H;
+    const int64_t R0 = total_rows * blockIdx.x / gridDim.x, R1 = total_rows * (blockIdx.x + 1) / gridDim.x;
+    const int nrows = (int)(R1 - R0);
+    if (nrows <= 0) return;
+    // ---- producer side (thread 0): one row = C soft planes + the id row
+    auto issue_row = [&](int64_t rr, int stage) {
+        const int bi = (int)(rr / H);
+        const int y = (int)(rr - (int64_t)bi * H);
+        unsigned char* dst = smem_raw + (size_t)stage * L.stage_bytes;
+        const float* src = p.soft + (int64_t)bi * C * HW + (int64_t)y * W;
+        if (UEM_REFINE_EXP == 1) return;
+        mbar_arrive_expect_tx(&full[stage], L.stage_bytes);
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) tma_load_1d(dst + (size_t)ci * W * 4, src + (int64_t)ci * HW, (uint32_t)W * 4u, &full[stage]);
+        tma_load_1d(dst + (size_t)C * W * 4, p.sup + (int64_t)bi * HW + (int64_t)y * W, (uint32_t)W * 8u, &full[stage]);
+    };
+    // ---- low-res rows i0/i1 of the 3C planes feeding output row (bi,y): 2*3C bulk copies of w*4 bytes issued by the
+    // lanes of warp 0, only when (image, i0) changes (every ~H/h output rows); vertical lerp per output row below
+    uint64_t* rawbar = &full[NSTAGE];
+    int raw_bi = -1, raw_i0 = -1;
+    uint32_t raw_fetches = 0;   // CTA-uniform: completed + outstanding fetches
+    bool raw_pending = false;
+    auto fetch_lowres = [&](int fbi, int fy) {
+        const Lerp ly = make_lerp(fy, p.h, p.sy);
+        if (fbi == raw_bi && ly.i0 == raw_i0) return;
+        raw_bi = fbi;
+        raw_i0 = ly.i0;
+        ++raw_fetches;
+        raw_pending = true;
+        if (wid == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(rawbar, 2u * 3u * C * (uint32_t)w * 4u);
+            if (lane < 3 * C) {
+                const int m = lane / C, ci = lane - m * C;
+                const float* plane = p.maps[m] + ((int64_t)fbi * C + ci) * hw_low;
+                tma_load_1d(raw + lane * w, plane + ly.i0 * w, (uint32_t)w * 4u, rawbar);
+                tma_load_1d(raw + (3 * C + lane) * w, plane + ly.i1 * w, (uint32_t)w * 4u, rawbar);
+            }
+        }
+    };
+    // thread -> (class ci = wid + NW*t, column x = lane + 32*s); map index and t are compile-time
+    auto lerp_lowres = [&](float* row, int ly_y) {
+        const Lerp ly = make_lerp(ly_y, p.h, p.sy);
+        if (raw_pending) { mbar_wait(rawbar, (raw_fetches - 1u) & 1u); raw_pending = false; }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const float sc = p.map_scale[m];
+            const bool dv = p.div_temp && m > 0;
+#pragma unroll
+            for (int t = 0; t < (C + NW - 1) / NW; ++t) {
+                const int ci = wid + NW * t;
+                if (ci < C) {
+                    const float* r0 = raw + (m * C + ci) * w;
+                    const float* r1 = r0 + 3 * C * w;
+                    float* d0 = row + m * CP + ci;
+                    for (int x = lane; x < w; x += 32) {
+                        const float v = ly.l0 * r0[x] + ly.l1 * r1[x];
+                        const float o = dv ? __fdiv_rn(v, p.temp) * kL2E : v * sc;
+                        float* d = d0 + x * STRIDE;
+                        d[0] = o;
+                        if (x == w - 1) { d[STRIDE] = o; d[2 * STRIDE] = o; }  // two replicated columns (tap a+2 always exists)
+                    }
+                }
+            }
+        }
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s <= NSTAGE; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();  // barriers initialised
+    int bi = (int)(R0 / H), y = (int)(R0 - (int64_t)bi * H);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE && s < nrows; ++s) issue_row(R0 + s, s);
+    }
+    fetch_lowres(bi, y);
+    // padded class slots: -1e30 -> EX2 gives exactly 0, never wins a max (written once, both tap rows)
+    if constexpr (CP > C) {
+        for (int i = threadIdx.x; i < 2 * (w + 2) * 3 * (CP - C); i += NT) {
+            const int slot = i % (CP - C), rest = i / (CP - C);
+            const int m = rest % 3, col = rest / 3;  // col runs over both buffers
+            rowbuf[col * STRIDE + m * CP + C + slot] = -1e30f;
+        }
+    }
+#if !UEM_XTAB_GLOBAL
+    for (int g = threadIdx.x; g < groups; g += NT) xtab_entry<C>(xtab + 4 * g, g, w, p.sx);
+#endif
+    lerp_lowres(rowbuf, y);
+    __syncthreads();
+
+    float cmax[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) cmax[ci] = -INFINITY;
+    float cmin = INFINITY;
+    bool bad = false;
+
+    for (int it = 0; it < nrows; ++it) {
+        const int stage = it % NSTAGE;
+        const uint32_t parity = (uint32_t)(it / NSTAGE) & 1u;
+        const float* row = rowbuf + (it & 1) * rowlen;
+        // next row's coordinates + its low-res fetch (in flight during this row's math)
+        int nbi = bi, ny = y + 1;
+        if (ny == H) { ny = 0; ++nbi; }
+        const bool has_next = it + 1 < nrows;
+        if (has_next) fetch_lowres(nbi, ny);
+        if (UEM_REFINE_EXP != 1) mbar_wait(&full[stage], parity);  // this row's soft planes + ids have landed (issued NSTAGE rows ago)
+
+        const float* soft_s = reinterpret_cast<const float*>(smem_raw + (size_t)stage * L.stage_bytes);
+        const longlong2* ids_s = reinterpret_cast<const longlong2*>(soft_s + (size_t)C * W);
+        float* outb = p.out + (int64_t)bi * C * HW + (int64_t)y * W;
+        const float4* swb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
+        const uint32_t Ru = (uint32_t)p.R;
+        float nanacc = 0.f;  // s*0 accumulates to NaN iff a row sum was inf/NaN
+        for (int g = threadIdx.x; g < groups; g += NT) {
+#if UEM_XTAB_GLOBAL
+            const float4 q0 = __ldg(xtab + g * 4), qa = __ldg(xtab + g * 4 + 1), qb = __ldg(xtab + g * 4 + 2), qc = __ldg(xtab + g * 4 + 3);
+#else
+            const float4 q0 = xtab[g * 4], qa = xtab[g * 4 + 1], qb = xtab[g * 4 + 2], qc = xtab[g * 4 + 3];
+#endif
+            const float wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w}, wc[4] = {qc.x, qc.y, qc.z, qc.w};
+            const float* col = row + __float_as_int(q0.x);
+            float2 wgt2[PC][4];
+#if UEM_REFINE_EXP == 2
+#pragma unroll
+            for (int j = 0; j < PC; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wgt2[j][i] = make_float2(wa[i] + col[0], wb[i]);
+#else
+            {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
+                float2 t[3][PC];
+                load_tap3p<C>(col, STRIDE, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
+                    float2 z[PC];
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) z[j] = UEM_FFMA2(c2, t[2][j], UEM_FFMA2(b2, t[1][j], UEM_FMUL2(a2, t[0][j])));
+                    const float S = exp2_shifted2<PC>(z);
+                    const float rs = fmaf(-1e-7f, S, 1.0f);
+                    const float2 rs2 = make_float2(rs, rs);
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) wgt2[j][i] = UEM_FMUL2(z[j], rs2);
+                }
+            }
+            {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7).  The 0.5 of the mean is
+                // folded into the epsilon (q/(max q + 2e-7) == (q/2)/(max q/2 + 1e-7), exact power-of-two scaling)
+                float2 t[3][PC], u[3][PC];
+                load_tap3p<C>(col + CP, STRIDE, t);
+                load_tap3p<C>(col + 2 * CP, STRIDE, u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
+                    float2 z[PC], z2[PC];
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        z[j] = UEM_FFMA2(c2, t[2][j], UEM_FFMA2(b2, t[1][j], UEM_FMUL2(a2, t[0][j])));
+                        z2[j] = UEM_FFMA2(c2, u[2][j], UEM_FFMA2(b2, u[1][j], UEM_FMUL2(a2, u[0][j])));
+                    }
+                    const float S1 = exp2_shifted2<PC>(z);
+                    const float S2 = exp2_shifted2<PC>(z2);
+                    const float h1 = rcp_approx(S1), h2 = rcp_approx(S2);
+                    const float2 h1v = make_float2(h1, h1), h2v = make_float2(h2, h2);
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        z[j] = UEM_FFMA2(z[j], h1v, UEM_FMUL2(z2[j], h2v));
+                        mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
+                    }
+                    const float inv = rcp_approx(mx + 2e-7f);
+                    const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) wgt2[j][i] = UEM_FFMA2(z[j], inv2, wgt2[j][i]);
+                }
+            }
+#endif
+            // superpixel view: multiplicative outside the ignored id (branch-free: its table row is all ones; an id
+            // outside [0,R) is redirected to the all-ones sentinel row R)
+            {
+                const longlong2 i01 = ids_s[2 * g], i23 = ids_s[2 * g + 1];
+                const int64_t rid[4] = {i01.x, i01.y, i23.x, i23.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t lo = (uint32_t)rid[i], hi = (uint32_t)((uint64_t)rid[i] >> 32);
+                    const uint32_t r = (hi == 0u && lo < Ru) ? lo : Ru;
+                    const float4* wp = swb + (size_t)r * (CP / 4);
+#pragma unroll
+                    for (int q = 0; q < CP / 4; ++q) {
+                        const float4 v = __ldg(wp + q);
+                        wgt2[2 * q][i] = UEM_FMUL2(wgt2[2 * q][i], make_float2(v.x, v.y));
+                        if (2 * q + 1 < PC) wgt2[2 * q + 1][i] = UEM_FMUL2(wgt2[2 * q + 1][i], make_float2(v.z, v.w));
+                    }
+                }
+            }
+            // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
+            float o[C][4];
+            {
+                const float* sp = soft_s + 4 * g;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float4 v = *reinterpret_cast<const float4*>(sp);
+                    sp += W;
+                    const float sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[ci][i] = ((ci & 1) ? wgt2[ci >> 1][i].y : wgt2[ci >> 1][i].x) * sv[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) s += o[ci][i];
+                const float inv = rcp_approx(s + 1e-7f);
+                nanacc = fmaf(s, 0.f, nanacc);
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) o[ci][i] *= inv;
+            }
+            float* op = outb + 4 * g;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                cmax[ci] = fmaxf(cmax[ci], fmaxf(fmaxf(o[ci][0], o[ci][1]), fmaxf(o[ci][2], o[ci][3])));
+                cmin = fminf(cmin, fminf(fminf(o[ci][0], o[ci][1]), fminf(o[ci][2], o[ci][3])));
+                stg_f4(op, make_float4(o[ci][0], o[ci][1], o[ci][2], o[ci][3]));
+                op += HW;
+            }
+        }
+        bad |= (nanacc != nanacc);
+        if (has_next) lerp_lowres(rowbuf + ((it + 1) & 1) * rowlen, ny);
+        __syncthreads();  // next tap row complete; everybody is done with this stage's soft/ids
+        if (threadIdx.x == 0 && it + NSTAGE < nrows) issue_row(R0 + it + NSTAGE, stage);
+        if (has_next && nbi != bi && p.stats) flush_stats<C>(p.stats, bi, cmax, cmin, bad, red);
+        bi = nbi;
+        y = ny;
+    }
+    if (p.stats) flush_stats<C>(p.stats, bi - (y == 0 ? 1 : 0), cmax, cmin, bad, red);
+}
+
+// superpixel-view weight of every (image, region): softmax(region_max/temp) / (max + 1e-7)  (alignment.py:252-253)
+// table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R+1,CP); the row of the ignored id and
+// row R (the sentinel out-of-range ids are redirected to) are all ones
+template <int C>
+__global__ void __launch_bounds__(256) region_weight_kernel(const void* __restrict__ table, int encoded, int b, int64_t R,
+                                                            const int64_t* __restrict__ ignored_ptr, float temp, float inv_temp,
+                                                            int div_temp, float* __restrict__ sw, float4* __restrict__ xtab,
+                                                            int groups, int w, float sx) {
     constexpr int CP = Lay<C>::CP;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < regions; r += (int64_t)gridDim.x * blockDim.x) {
+    if (xtab)  // horizontal-weight table of the TMA refine kernel (depends on the column only)
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) xtab_entry<C>(xtab + 4 * g, g, w, sx);
+    const int64_t rows = (int64_t)b * (R + 1);
+    const int64_t ignored = *ignored_ptr;  // the batch-global max id: weight 1 (alignment.py:255 leaves those pixels alone)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bi = i / (R + 1), rl = i - bi * (R + 1);
+        float4* dst = reinterpret_cast<float4*>(sw + i * CP);
+        if (rl == R || rl == ignored) {
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+            continue;
+        }
+        const int64_t r = bi * R + rl;
         float z[C];
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) {
@@ -458,8 +751,11 @@ __global__ void __launch_bounds__(256) region_weight_kernel(const void* __restri
         }
         const float S = exp_shifted<C>(z);
         const float rs = fmaf(-1e-7f, S, 1.0f);
+        float o[CP];
 #pragma unroll
-        for (int ci = 0; ci < CP; ++ci) sw[r * CP + ci] = ci < C ? z[ci < C ? ci : 0] * rs : 0.f;
+        for (int ci = 0; ci < CP; ++ci) o[ci] = ci < C ? z[ci < C ? ci : 0] * rs : 0.f;
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     }
 }
 
@@ -509,24 +805,54 @@ static int sm_count() {
 }
 
 template <typename K>
-static int launch_persistent(K kernel, const RefineParams& p, size_t smem, cudaStream_t st) {
+static int launch_persistent(K kernel, const RefineParams& p, int threads, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRefineThreads, smem));
+    UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t total_rows = (int64_t)p.b * p.H;
     const int grid = (int)min(total_rows, (int64_t)sm_count() * per_sm);
-    kernel<<<grid, kRefineThreads, smem, st>>>(p);
+    kernel<<<grid, threads, smem, st>>>(p);
     return 0;
 }
 
-// sw_ws: b*R*CP floats of scratch for the per-region weights (superpixel view only)
+// TMA-fed kernel: NT = 128 threads for rows up to 512 pixels, 256 beyond (a row is one pass of the CTA);
+// two rows in flight per CTA unless a third fits without costing a resident CTA
+template <int C>
+static int launch_refine_tma(RefineParams p, cudaStream_t st, bool* done) {
+    *done = false;
+    const int groups = p.W / 4;
+    const int nt = groups > 128 ? 256 : 128;
+    const size_t s2 = tma_layout(C, p.W, p.w, 2).total, s3 = tma_layout(C, p.W, p.w, 3).total;
+    const size_t budget = 200 * 1024;
+    if (s2 > budget) return 0;  // row too long for two stages: generic kernel
+    constexpr float kL2E = 1.4426950408889634f;
+    p.map_scale[0] = kL2E;
+    p.map_scale[1] = p.map_scale[2] = kL2E / p.temp;  // used when temp is a power of two (exact scaling)
+    const size_t per2 = (228 * 1024) / (s2 + 1024 + 256), per3 = (228 * 1024) / (s3 + 1024 + 256);
+#ifdef UEM_REFINE_FORCE3
+    const bool three = s3 <= budget;
+#else
+    const bool three = s3 <= budget && per3 >= per2;
+#endif
+    int rc;
+    if (nt == 128) {
+        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 128>, p, 128, s3, st) : launch_persistent(refine_tma_kernel<C, 2, 128>, p, 128, s2, st);
+    } else {
+        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 256>, p, 256, s3, st) : launch_persistent(refine_tma_kernel<C, 2, 256>, p, 256, s2, st);
+    }
+    *done = (rc == 0);
+    return rc;
+}
+
+// sw_ws: b*(R+1)*CP floats of scratch for the per-region weights (superpixel view only)
 static int launch_refine(int views, const float* simi, const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                          const void* table, int table_encoded, int64_t R, const int64_t* ignored_id, const float* soft, int b,
                          int c, int H, int W, float temp, float* out, unsigned* stats, float* sw_ws, cudaStream_t st) {
     UEM_REQUIRE(soft && out && b > 0 && H > 0 && W > 0, "uem_label_refine_f32: bad arguments");
     UEM_REQUIRE(views > 0 && views < 8, "uem_label_refine_f32: views must be a non-empty mask of UEM_VIEW_*");
     UEM_REQUIRE(temp > 0.f, "uem_label_refine_f32: temp must be > 0");  // alignment.py:313
+    UEM_REQUIRE(R < ((int64_t)1 << 30), "uem_label_refine_f32: region capacity %lld too large", (long long)R);
     RefineParams p{};
     p.views = views;
     int ex;
@@ -553,24 +879,31 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     p.sup = sup; p.sw = sw_ws; p.R = R; p.ignored_id = ignored_id;
     p.soft = soft; p.out = out; p.stats = stats;
     const bool vec = (W % 4 == 0) && uem_aligned16(soft) && uem_aligned16(out) && (!sup || uem_aligned16(sup));
-    const bool fast = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2 && 3.0f * p.sx <= 0.999f;
+    const bool fast = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2 && 3.0f * p.sx <= 0.999f &&
+                      (w % 4 == 0) && uem_aligned16(simi) && uem_aligned16(pred1) && uem_aligned16(pred2);
+    float4* xt = sw_ws ? reinterpret_cast<float4*>(sw_ws + (int64_t)b * (R + 1) * cp_of(c)) : nullptr;  // 16-byte aligned (CP % 4 == 0)
+    p.xtab = xt;
     void *ev0 = nullptr, *ev1 = nullptr;
     int launched = 1, rc = 0;
     UEM_DISPATCH_C(c, {
         if (views & UEM_VIEW_SUP) {
-            const int64_t regions = (int64_t)b * R;
-            region_weight_kernel<C><<<(int)min((int64_t)UEM_SMS * 4, (regions + 255) / 256), 256, 0, st>>>(
-                table, table_encoded, regions, temp, 1.0f / temp, p.div_temp, sw_ws);
+            const int64_t rows = (int64_t)b * (R + 1);
+            region_weight_kernel<C><<<(int)min((int64_t)UEM_SMS * 4, (rows + 255) / 256), 256, 0, st>>>(
+                table, table_encoded, b, R, ignored_id, temp, 1.0f / temp, p.div_temp, sw_ws,
+                (UEM_XTAB_GLOBAL && fast) ? xt : nullptr, W / 4, w, p.sx);
             launched = 2;
         }
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
-        const int vecw = vec ? 4 : 1;
-        const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
-        UEM_REQUIRE(smem <= 200 * 1024, "uem_label_refine_f32: low-res width %d too large", w);
-        if (fast) rc = launch_persistent(refine_kernel<C, 4, true>, p, smem, st);
-        else if (vec) rc = launch_persistent(refine_kernel<C, 4, false>, p, smem, st);
-        else rc = launch_persistent(refine_kernel<C, 1, false>, p, smem, st);
+        bool done = false;
+        if (fast) rc = launch_refine_tma<C>(p, st, &done);
+        if (!done && rc == 0) {
+            const int vecw = vec ? 4 : 1;
+            const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
+            UEM_REQUIRE(smem <= 200 * 1024, "uem_label_refine_f32: low-res width %d too large", w);
+            if (vec) rc = launch_persistent(refine_kernel<C, 4>, p, kRefineThreads, smem, st);
+            else rc = launch_persistent(refine_kernel<C, 1>, p, kRefineThreads, smem, st);
+        }
     });
     if (rc) return rc;
     if (ev1) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev1, st));
@@ -582,7 +915,9 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
 
 extern "C" int64_t uem_class_stats_bytes(int b, int c) { return align16((int64_t)b * (c + 2) * 4); }
 
-extern "C" int64_t uem_label_refine_ws_bytes(int b, int c, int64_t R) { return align16((int64_t)b * (R > 0 ? R : 1) * cp_of(c) * 4); }
+extern "C" int64_t uem_label_refine_ws_bytes(int b, int c, int64_t R, int W) {
+    return align16((int64_t)b * ((R > 0 ? R : 0) + 1) * cp_of(c) * 4) + align16((int64_t)(W / 4 + 1) * 64);
+}
 
 extern "C" int uem_label_refine_f32(int views, const float* simi, const float* pred1, const float* pred2, int h, int w,
                                     const int64_t* sup, const float* region_max, int64_t R, const int64_t* ignored_id,
@@ -622,12 +957,12 @@ extern "C" int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, cons
 struct MineLayout {
     int64_t simi, pearson, sw, zero_begin, maxid, stats, region, end;
 };
-static MineLayout mine_layout(int b, int c, int h, int w, int k, int64_t R) {
+static MineLayout mine_layout(int b, int c, int W, int h, int w, int k, int64_t R) {
     MineLayout L;
     int64_t n = 16;
     L.simi = n; n += align16((int64_t)b * c * h * w * 4);
     L.pearson = n; n += align16(uem_pearson_ws_bytes(c, k));
-    L.sw = n; n += uem_label_refine_ws_bytes(b, c, R);
+    L.sw = n; n += uem_label_refine_ws_bytes(b, c, R, W);
     L.zero_begin = n;
     L.maxid = n; n += 16;
     L.stats = n; n += uem_class_stats_bytes(b, c);
@@ -637,12 +972,12 @@ static MineLayout mine_layout(int b, int c, int h, int w, int k, int64_t R) {
 }
 
 extern "C" int64_t uem_mine_ws_bytes(int b, int c, int H, int W, int h, int w, int k, int64_t R) {
-    (void)H; (void)W;
-    return mine_layout(b, c, h, w, k, R).end;
+    (void)H;
+    return mine_layout(b, c, W, h, w, k, R).end;
 }
 extern "C" int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R) {
-    (void)H; (void)W;
-    return mine_layout(b, c, h, w, k, R).stats;
+    (void)H;
+    return mine_layout(b, c, W, h, w, k, R).stats;
 }
 
 extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos, const float* pred1,
@@ -654,7 +989,7 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     UEM_REQUIRE(ws && soft && refined, "uem_mine_refine_select_f32: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
-    const MineLayout L = mine_layout(b, c, h, w, k, R);
+    const MineLayout L = mine_layout(b, c, W, h, w, k, R);
     int* status = (int*)base;
     float* simi = (float*)(base + L.simi);
     void* pws = base + L.pearson;

@@ -285,7 +285,7 @@ def label_refine(views, soft, temp, simi=None, pred1=None, pred2=None, sup=None,
     R = region_max.shape[1] if region_max is not None else 0
     out = torch.empty_like(soft)
     stats = torch.zeros((b, c + 2), dtype=torch.int32, device=soft.device) if want_stats else None
-    ws = L.workspace(lib.uem_label_refine_ws_bytes(b, c, R), soft)
+    ws = L.workspace(lib.uem_label_refine_ws_bytes(b, c, R, W), soft)
     L.check(lib.uem_label_refine_f32(int(views), L.ptr(simi), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), L.ptr(region_max),
                                      R, L.ptr(ignored_id), L.ptr(soft), b, c, H, W, f32(temp), L.ptr(out), L.ptr(stats),
                                      L.ptr(ws), L.stream_of(soft)))
