@@ -78,22 +78,24 @@ def main():
         for s in sets:
             fn(s)
         torch.cuda.synchronize()
-        graphs, keep = [], []
-        for s in sets:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                keep.append(fn(s))
-            graphs.append(g)
-        for g in graphs:
-            g.replay()
+        # ONE graph holding `reps` back-to-back calls (rotating over the input sets): graph-launch latency on the host
+        # (several us) would otherwise dominate the short kernels
+        reps = 4 * len(sets)
+        keep = []
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                keep.append(fn(sets[i % len(sets)]))
+        g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rep = max(1, args.iters // reps)
         e0.record()
-        for i in range(args.iters):
-            graphs[i % len(graphs)].replay()
+        for i in range(n_rep):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / args.iters
+        us = e0.elapsed_time(e1) * 1e3 / (n_rep * reps)
         gbs = nbytes / us / 1e3
         print("%-20s %10.2f %10.1f %7.1f%%" % (name, us, gbs, 100 * gbs / 6536.7), flush=True)
 

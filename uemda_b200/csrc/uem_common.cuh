@@ -181,6 +181,36 @@ static inline float uem_align_corners_scale(int in_size, int out_size) {
     return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;
 }
 
+// single-MUFU approximations (2 ulp): reciprocal and 2^x
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+#ifdef UEM_NO_MUFU
+    return fmaf(x, x, 1.0f);  // development experiment only: takes the XU pipe out of the picture
+#else
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+// e_c = exp(z_c - max z) (one MUFU each; results below 2^-126 flush to 0, irrelevant for a softmax numerator),
+// returns S = sum e_c
+template <int C> __device__ __forceinline__ float exp_shifted(float (&z)[C]) {
+    float mx = z[0];
+#pragma unroll
+    for (int i = 1; i < C; ++i) mx = fmaxf(mx, z[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        z[i] = ex2_approx((z[i] - mx) * 1.4426950408889634f);
+        s += z[i];
+    }
+    return s;
+}
+
 // softmax over a register vector: y = exp(x - max) / sum, matches torch.softmax to ~2 ulp
 template <int C> __device__ __forceinline__ void softmax_regs(float (&x)[C]) {
     float mx = x[0];

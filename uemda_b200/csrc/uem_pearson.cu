@@ -9,6 +9,9 @@
 // where pc_j is the centred prototype (sum_k pc_j ~ 0, so centring f is unnecessary for the covariance;
 // the residual mean(g)*sum(pc_j) is subtracted anyway).  HBM-bound on feat: 4k B per feature pixel.
 #include "uem_common.cuh"
+#include "uem_tma.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -175,6 +178,147 @@ __global__ void __launch_bounds__(kPearsonThreads, 4) pearson_nchw_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA form (hw % 4 == 0): the NCHW map is streamed as [kKT channels x kPT pixels] tiles (cp.async.bulk.tensor,
+// 16 KB each) through a kStages-deep mbarrier ring filled by a dedicated producer warp; 8 consumer warps keep the
+// 2+M running sums of their 4 pixels in registers (packed FFMA2 over pixel pairs, the centred prototype as the
+// scalar operand).  The k dimension is split over the CTAs of a thread-block cluster; the partial sums are
+// combined through distributed shared memory (no global scratch, no atomics) and rank 0 finishes the distance.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPT = 128;      // pixels per tile (512 B rows)
+constexpr int kKT = 32;       // channels per tile
+constexpr int kStages = 4;    // tiles in flight per CTA (64 KB)
+constexpr int kConsumers = 256;
+constexpr int kTmaThreads = kConsumers + 32;
+
+template <int M>
+__global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ feat,
+                                                                  int k, int hw, int kper, const float* __restrict__ pc,
+                                                                  const float* __restrict__ stats, float eps, int reciprocal,
+                                                                  float* __restrict__ out) {
+    constexpr int NA = 2 + M;
+    extern __shared__ __align__(128) unsigned char smem_p[];
+    float* tiles = reinterpret_cast<float*>(smem_p);                                   // [kStages][kKT][kPT]
+    float* pcs = tiles + (size_t)kStages * kKT * kPT;                                  // [kStages][kKT][kPcStride] centred prototypes
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_p + (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4);
+    uint64_t* empty = full + kStages;
+    float* part = reinterpret_cast<float*>(empty + kStages);                           // [NA][kPT] CTA partial (cluster-visible)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int ks = (int)cluster.block_rank(), KS = (int)cluster.num_blocks();
+    const int ptile = blockIdx.x / KS, bi = blockIdx.y;
+    const int px0 = ptile * kPT;
+    const int kbeg = ks * kper, kend = min(k, kbeg + kper);
+    const int ntiles = kend > kbeg ? (kend - kbeg + kKT - 1) / kKT : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumers / 32) {
+        // ---- producer warp: one lane streams the tiles of this CTA's channel range
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages, r = t / kStages;
+                if (r > 0) mbar_wait(&empty[s], (uint32_t)(r - 1) & 1u);
+                const int kk0 = kbeg + t * kKT;
+                const uint32_t pc_bytes = (uint32_t)min(kKT, k - kk0) * kPcStride * 4u;  // the tile's rows of the (k,8) table
+                mbar_arrive_expect_tx(&full[s], kKT * kPT * 4 + pc_bytes);
+                tma_load_3d(tiles + (size_t)s * kKT * kPT, &tmap, px0, kk0, bi, &full[s]);
+                tma_load_1d(pcs + (size_t)s * kKT * kPcStride, pc + (int64_t)kk0 * kPcStride, pc_bytes, &full[s]);
+            }
+        }
+        __syncwarp();  // the warp re-converges before the (aligned) cluster barrier below
+    } else {
+        // ---- consumers: warp -> channels warp, warp+8, .. of the tile; lane -> 4 consecutive pixels
+        const int px = px0 + lane * 4;
+        const bool inb = px < hw;  // hw % 4 == 0
+        float2 piv01 = make_float2(0.f, 0.f), piv23 = make_float2(0.f, 0.f);
+        if (inb) {  // channel 0 of these pixels: the shift that keeps the one-pass variance stable (same for every k split)
+            const float4 pv = ldg_f4(feat + (int64_t)bi * k * hw + px);
+            piv01 = make_float2(-pv.x, -pv.y);
+            piv23 = make_float2(-pv.z, -pv.w);
+        }
+        float2 acc[NA][2];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) { acc[a][0] = make_float2(0.f, 0.f); acc[a][1] = make_float2(0.f, 0.f); }
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % kStages;
+            mbar_wait(&full[s], (uint32_t)(t / kStages) & 1u);
+            const float* tile = tiles + (size_t)s * kKT * kPT + lane * 4;
+            const float* pct = pcs + (size_t)s * kKT * kPcStride;
+            const int kk0 = kbeg + t * kKT;
+#pragma unroll
+            for (int j = 0; j < kKT / 8; ++j) {
+                const int row = warp + 8 * j, kk = kk0 + row;
+                if (kk < kend) {
+                    const float4 v = *reinterpret_cast<const float4*>(tile + row * kPT);
+                    const float4 p0 = *reinterpret_cast<const float4*>(pct + row * kPcStride);  // broadcast LDS.128
+                    float pcv[kPcStride];
+                    pcv[0] = p0.x; pcv[1] = p0.y; pcv[2] = p0.z; pcv[3] = p0.w;
+                    if (M > 4) {
+                        const float4 p1 = *reinterpret_cast<const float4*>(pct + row * kPcStride + 4);
+                        pcv[4] = p1.x; pcv[5] = p1.y; pcv[6] = p1.z; pcv[7] = p1.w;
+                    }
+                    const float2 g01 = __fadd2_rn(make_float2(v.x, v.y), piv01), g23 = __fadd2_rn(make_float2(v.z, v.w), piv23);
+                    acc[0][0] = __fadd2_rn(acc[0][0], g01);
+                    acc[0][1] = __fadd2_rn(acc[0][1], g23);
+                    acc[1][0] = __ffma2_rn(g01, g01, acc[1][0]);
+                    acc[1][1] = __ffma2_rn(g23, g23, acc[1][1]);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float2 pm = make_float2(pcv[m], pcv[m]);
+                        acc[2 + m][0] = __ffma2_rn(g01, pm, acc[2 + m][0]);
+                        acc[2 + m][1] = __ffma2_rn(g23, pm, acc[2 + m][1]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- fold the 8 warps (channel sub-slices) of this CTA: red[warp][NA][pixel] in the drained tile ring
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");  // every consumer is past its last tile read
+        float* red = tiles;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+            *reinterpret_cast<float4*>(red + ((size_t)warp * NA + a) * kPT + lane * 4) =
+                make_float4(acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y);
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+        if (threadIdx.x < kPT) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                float sum = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < kConsumers / 32; ++wv) sum += red[((size_t)wv * NA + a) * kPT + threadIdx.x];
+                part[a * kPT + threadIdx.x] = sum;
+            }
+        }
+    }
+    // ---- fold the k splits across the cluster through distributed shared memory; rank 0 finishes
+    cluster.sync();
+    if (ks == 0 && threadIdx.x < kPT) {
+        const int px = px0 + threadIdx.x;
+        float sacc[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) sacc[a] = part[a * kPT + threadIdx.x];
+        for (int r = 1; r < KS; ++r) {
+            const float* rp = cluster.map_shared_rank(part, r);
+#pragma unroll
+            for (int a = 0; a < NA; ++a) sacc[a] += rp[a * kPT + threadIdx.x];
+        }
+        if (px < hw) {
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+                out[((int64_t)bi * M + j) * hw + px] =
+                    pearson_finish(sacc[0], sacc[1], sacc[2 + j], stats[2 * j], stats[2 * j + 1], k, eps, reciprocal);
+        }
+    }
+    cluster.sync();  // remote partials stay alive until rank 0 has read them
+}
+
 // generic row-major (n,k) x (m,k): one warp per feat1 row, classes in chunks of 8
 __global__ void __launch_bounds__(256) pearson_rows_kernel(const float* __restrict__ f1, int64_t n, int k, const float* __restrict__ pc,
                                                            const float* __restrict__ stats, int m, float eps, float* __restrict__ out) {
@@ -225,9 +369,36 @@ extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_
     float* stats = pc + (int64_t)kPcStride * k;
     const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
     UEM_CUDA(cudaMemsetAsync(pc, 0, (size_t)kPcStride * k * sizeof(float), st));  // unused class slots stay 0
+    const bool tma = vec && hw < (1 << 30) && k >= kKT;
     UEM_DISPATCH_C(m, {
         proto_center_kernel<<<C, 256, 0, st>>>(protos, k, 1, pc, stats);
-        if (vec) {
+        if (tma) {
+            CUtensorMap tmap;
+            UEM_REQUIRE(uem_make_tmap_3d_f32(&tmap, feat, (uint64_t)hw, (uint64_t)k, (uint64_t)b, (uint64_t)hw, (uint64_t)k * hw, kPT,
+                                             kKT) == 0,
+                        "uem_pearson_dist_nchw_f32: cuTensorMapEncodeTiled failed");
+            const int ptiles = uem_div_up(hw, kPT);
+            // split k over a cluster so that ~2 CTAs per SM are busy, each with at least 4 tiles of its own
+            int KS = 1;
+            while (KS < 8 && (int64_t)ptiles * b * KS * 2 <= 2 * UEM_SMS && k / (KS * 2) >= 4 * kKT) KS *= 2;
+            const int kper = ((k + KS - 1) / KS + kKT - 1) / kKT * kKT;
+            const size_t smem = (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4 + 2 * kStages * 8 + (size_t)kPT * (2 + C) * 4;
+            UEM_CUDA(cudaFuncSetAttribute(pearson_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ptiles * KS, b, 1);
+            cfg.blockDim = dim3(kTmaThreads, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = KS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            UEM_CUDA(cudaLaunchKernelEx(&cfg, pearson_tma_kernel<C>, tmap, feat, k, (int)hw, kper, (const float*)pc, (const float*)stats,
+                                        eps, reciprocal, out));
+        } else if (vec) {
             dim3 grid(uem_div_up(hw, kPxLanes * 4), b);
             pearson_nchw_kernel<C, 4><<<grid, kPearsonThreads, 0, st>>>(feat, k, hw, pc, stats, eps, reciprocal, out);
         } else {

@@ -9,6 +9,11 @@
 // channel) row, 128-bit loads, class ids staged as bytes in shared memory, c register accumulators)
 // and are combined over the batch in a fixed order, so results are bit-reproducible run to run.
 #include "uem_common.cuh"
+#include "uem_tma.cuh"
+
+#ifndef UEM_PROTO_RW
+#define UEM_PROTO_RW 4   // channel rows per consumer warp of the TMA accumulate kernel (item = 8*RW channels of one image)
+#endif
 
 namespace {
 
@@ -73,6 +78,70 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
         const float ratio = __fdiv_rn((float)best, area);   // avg_pool2d of the one-hot: count / (s*s)
         int64_t o = (arg == C || ratio < min_ratio) ? ignore_label : (int64_t)arg;
         out[((int64_t)bi * h + oy) * w + cx] = o;
+    }
+}
+
+// Power-of-two scale factors (the reference hard-wires 16): s/2 consecutive lanes own one output cell, each lane
+// streams its two columns over the s rows with independent 128-bit loads (16 in flight), and counts classes in packed
+// 16-bit fields (two 64-bit registers hold bins 0..7, bin 8 separately), so a label costs a shift and an add instead
+// of C+1 compares.  The lanes of a cell fold their counters with xor-shuffles; lane 0 takes the first-index argmax.
+template <int C>
+__global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
+                                                             int64_t cells, int64_t ignore_label, float min_ratio,
+                                                             int64_t* __restrict__ out, int32_t* __restrict__ status) {
+    const int tpc = s >> 1;  // lanes per cell (1..32)
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t cell = gid / tpc;
+    const int sub = (int)(gid - cell * tpc);
+    const bool live = cell < cells;
+    unsigned long long lo = 0ull, hi = 0ull;
+    unsigned b8 = 0u;
+    int bad = 0;
+    int ox = 0, oy = 0, bi = 0;
+    if (live) {
+        ox = (int)(cell % w);
+        const int64_t t = cell / w;
+        oy = (int)(t % h);
+        bi = (int)(t / h);
+        const int64_t* base = label + ((int64_t)bi * H + (int64_t)oy * s) * W + (int64_t)ox * s + sub * 2;
+        auto add = [&](int64_t v) {
+            const bool ign = (v == ignore_label);
+            const bool oob = !ign && (v < 0 || v >= C);
+            bad |= oob;
+            const int bin = ign ? C : (int)v;  // ignore -> bin C (alignment.py:497)
+            if (!oob) {
+                const unsigned long long one = 1ull << ((bin & 3) * 16);
+                if (bin < 4) lo += one;
+                else if (bin < 8) hi += one;
+                else ++b8;
+            }
+        };
+        for (int r0 = 0; r0 < s; r0 += 16) {
+            int64_t a[16], c2[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r0 + r < s) ldg_i64x2(base + (int64_t)(r0 + r) * W, a[r], c2[r]);
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r0 + r < s) { add(a[r]); add(c2[r]); }
+        }
+    }
+    for (int o = tpc >> 1; o > 0; o >>= 1) {
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        b8 += __shfl_xor_sync(0xffffffffu, b8, o);
+    }
+    if (bad && status) atomicOr(status, 1);
+    if (live && sub == 0) {
+        unsigned best = (unsigned)(lo & 0xffffu);
+        int arg = 0;
+#pragma unroll
+        for (int ci = 1; ci <= C; ++ci) {
+            const unsigned v = ci < 4 ? (unsigned)((lo >> (16 * ci)) & 0xffffu) : (ci < 8 ? (unsigned)((hi >> (16 * (ci - 4))) & 0xffffu) : b8);
+            if (v > best) { best = v; arg = ci; }  // first index wins ties (torch.max)
+        }
+        const float ratio = __fdiv_rn((float)best, (float)(s * s));  // avg_pool2d of the one-hot: count / (s*s)
+        out[((int64_t)bi * h + oy) * w + ox] = (arg == C || ratio < min_ratio) ? ignore_label : (int64_t)arg;
     }
 }
 
@@ -252,6 +321,142 @@ __global__ void __launch_bounds__(kAccThreads, 2) proto_accum_ring_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA form of the masked class sums (hw % 4 == 0): persistent CTAs loop over (image, block of 8*RW channels) items
+// and stream each item's [8*RW channels x 128 pixels] tiles (cp.async.bulk.tensor) through an mbarrier ring.
+// The producer warp also turns the int64 labels of the tile's 128 pixels into C one-hot fp32 planes (published with
+// the same full-barrier arrival as the tile), so the 8 consumer warps only do LDS.128 + packed FFMA2:
+//     acc2[row][class] += (mask.x,mask.y)*(v.x,v.y) ; += (mask.z,mask.w)*(v.z,v.w)
+// Per-image partial sums are folded afterwards in image order (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTilePx = 128;
+constexpr int kTmaConsumers = 256;
+constexpr int kTmaThreads = kTmaConsumers + 32;
+
+template <int C, int RW>
+struct ProtoTma {
+    static constexpr int ROWS = 8 * RW;                      // channels per item / tile
+    static constexpr int STAGES = 64 / ROWS * 2 > 8 ? 8 : 64 / ROWS * 2;  // ~64 KB of tiles in flight
+    static constexpr int TILE_BYTES = ROWS * kTilePx * 4;
+    static constexpr int MASK_BYTES = C * kTilePx * 4;
+    static constexpr size_t SMEM = (size_t)STAGES * (TILE_BYTES + MASK_BYTES) + 2 * STAGES * 8;
+};
+
+template <int C, int RW>
+__global__ void __launch_bounds__(kTmaThreads) proto_accum_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, int hw, int b,
+                                                                      const int64_t* __restrict__ label, int64_t ignore_label,
+                                                                      float* __restrict__ partial, int* __restrict__ cnt_partial) {
+    using P = ProtoTma<C, RW>;
+    extern __shared__ __align__(128) unsigned char smem_q[];
+    float* tiles = reinterpret_cast<float*>(smem_q);                                              // [STAGES][ROWS][128]
+    float* masks = reinterpret_cast<float*>(smem_q + (size_t)P::STAGES * P::TILE_BYTES);          // [STAGES][C][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_q + (size_t)P::STAGES * (P::TILE_BYTES + P::MASK_BYTES));
+    uint64_t* empty = full + P::STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (k + P::ROWS - 1) / P::ROWS, ntiles = (hw + kTilePx - 1) / kTilePx;
+    const int total = b * nkb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTmaConsumers / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t T = 0;  // tiles handled so far by this CTA (ring position), same sequence on both sides
+    if (warp == kTmaConsumers / 32) {
+        if (lane == 0) tma_prefetch_desc(&tmap);
+        // the labels of the NEXT tile are fetched while the current one waits for its ring slot, so the label round trip
+        // never sits between two TMA issues
+        auto fetch_labels = [&](int item, int t, int64_t (&l)[4]) {
+            l[0] = l[1] = l[2] = l[3] = ignore_label;
+            if (item < total) {
+                const int bi = item / nkb;
+                const int px = t * kTilePx + lane * 4;
+                if (px < hw) load_ids<4>(label + (int64_t)bi * hw + px, l);  // hw % 4 == 0
+            }
+        };
+        int64_t l[4];
+        fetch_labels(blockIdx.x, 0, l);
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int bi = item / nkb, kb = item - bi * nkb;
+            int cnt[C];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) cnt[ci] = 0;
+            for (int t = 0; t < ntiles; ++t, ++T) {
+                const uint32_t s = T % P::STAGES, r = T / P::STAGES;
+                int64_t ln[4];
+                if (t + 1 < ntiles) fetch_labels(item, t + 1, ln);
+                else fetch_labels(item + gridDim.x, 0, ln);
+                if (r > 0) mbar_wait(&empty[s], (r - 1) & 1u);
+                float* mk = masks + (size_t)s * C * kTilePx + lane * 4;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    float4 m;
+                    m.x = (l[0] == ci && l[0] != ignore_label) ? 1.f : 0.f;
+                    m.y = (l[1] == ci && l[1] != ignore_label) ? 1.f : 0.f;
+                    m.z = (l[2] == ci && l[2] != ignore_label) ? 1.f : 0.f;
+                    m.w = (l[3] == ci && l[3] != ignore_label) ? 1.f : 0.f;
+                    *reinterpret_cast<float4*>(mk + ci * kTilePx) = m;
+                    cnt[ci] += (int)(m.x + m.y + m.z + m.w);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[s], P::TILE_BYTES);
+                    tma_load_3d(tiles + (size_t)s * P::ROWS * kTilePx, &tmap, t * kTilePx, kb * P::ROWS, bi, &full[s]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) l[i] = ln[i];
+            }
+            if (kb == 0) {  // class counts of this image, once
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const int n = __reduce_add_sync(0xffffffffu, cnt[ci]);
+                    if (lane == 0) cnt_partial[bi * C + ci] = n;
+                }
+            }
+        }
+    } else {
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int bi = item / nkb, kb = item - bi * nkb;
+            float2 acc2[RW][C];
+#pragma unroll
+            for (int q = 0; q < RW; ++q)
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) acc2[q][ci] = make_float2(0.f, 0.f);
+            for (int t = 0; t < ntiles; ++t, ++T) {
+                const uint32_t s = T % P::STAGES;
+                mbar_wait(&full[s], (T / P::STAGES) & 1u);
+                const float* tile = tiles + (size_t)s * P::ROWS * kTilePx + (size_t)(warp * RW) * kTilePx + lane * 4;
+                const float* mk = masks + (size_t)s * C * kTilePx + lane * 4;
+                float4 v[RW];
+#pragma unroll
+                for (int q = 0; q < RW; ++q) v[q] = *reinterpret_cast<const float4*>(tile + q * kTilePx);
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float4 m = *reinterpret_cast<const float4*>(mk + ci * kTilePx);
+                    const float2 m01 = make_float2(m.x, m.y), m23 = make_float2(m.z, m.w);
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) {
+                        acc2[q][ci] = __ffma2_rn(m01, make_float2(v[q].x, v[q].y), acc2[q][ci]);
+                        acc2[q][ci] = __ffma2_rn(m23, make_float2(v[q].z, v[q].w), acc2[q][ci]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                const int kk = kb * P::ROWS + warp * RW + q;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float x = warp_sum(acc2[q][ci].x + acc2[q][ci].y);
+                    if (lane == 0 && kk < k) partial[((int64_t)bi * C + ci) * k + kk] = x;
+                }
+            }
+        }
+    }
+}
+
 // soft weights: bilinear (align_corners=True) down-sampling of soft (b,C,H,W) to (h,w) (alignment.py:102)
 __global__ void __launch_bounds__(256) soft_down_kernel(const float* __restrict__ soft, int planes, int H, int W, int h, int w,
                                                         float sy, float sx, float* __restrict__ down) {
@@ -344,6 +549,16 @@ extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W
     if (h == 0 || w == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int vec = (W % 2 == 0) && uem_aligned16(label) && (scale % 2 == 0);
+    if (vec && (scale & (scale - 1)) == 0 && scale <= 64) {  // power of two: packed-counter kernel
+        const int64_t cells = (int64_t)b * h * w;
+        const int64_t threads = cells * (scale / 2);
+        UEM_DISPATCH_C(n_classes, {
+            downscale_pow2_kernel<C><<<uem_div_up(threads, 256), 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out,
+                                                                             status);
+        });
+        UEM_CHECK_LAUNCH();
+        return 0;
+    }
     // enough CTAs for ~4 waves: split every output row into column segments of whole cells
     int nseg = (int)min((int64_t)w, max((int64_t)1, (int64_t)(4 * UEM_SMS + (int64_t)h * b - 1) / ((int64_t)h * b)));
     nseg = min(nseg, 64);
@@ -380,7 +595,21 @@ extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t
     const size_t smem = (size_t)((hw + 15) / 16) * 16;
     UEM_DISPATCH_C(c, {
         dim3 grid(uem_div_up(k, (kAccThreads / 32) * kChPerWarp), b);
-        if (vec) {
+        if (vec && hw < (1 << 30)) {
+            using P = ProtoTma<C, UEM_PROTO_RW>;
+            CUtensorMap tmap;
+            UEM_REQUIRE(uem_make_tmap_3d_f32(&tmap, feat, (uint64_t)hw, (uint64_t)k, (uint64_t)b, (uint64_t)hw, (uint64_t)k * hw, kTilePx,
+                                             P::ROWS) == 0,
+                        "uem_proto_accum_nchw_f32: cuTensorMapEncodeTiled failed");
+            UEM_CUDA(cudaFuncSetAttribute(proto_accum_tma_kernel<C, UEM_PROTO_RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+            int per_sm = 0;
+            UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, proto_accum_tma_kernel<C, UEM_PROTO_RW>, kTmaThreads, P::SMEM));
+            if (per_sm < 1) per_sm = 1;
+            const int total = b * uem_div_up(k, P::ROWS);
+            const int nblk = min(total, UEM_SMS * per_sm);
+            proto_accum_tma_kernel<C, UEM_PROTO_RW><<<nblk, kTmaThreads, P::SMEM, st>>>(tmap, k, (int)hw, b, label, ignore_label, partial,
+                                                                                         cnt_partial);
+        } else if (vec) {
             const int tile_px = (int)min((int64_t)kMaskTile, ((hw + 3) / 4) * 4);
             const size_t smem_r = (size_t)C * tile_px * 4 + (size_t)kRing * kChPerWarp * kAccThreads * 16;
             UEM_CUDA(cudaFuncSetAttribute(proto_accum_ring_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));

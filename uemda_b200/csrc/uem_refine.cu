@@ -25,11 +25,18 @@
 //     table updated with one atomicMax per class per CTA.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
+#include <stdlib.h>
 
 int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, const int64_t* index, int b, int64_t N,
                          int c, int64_t R, int op, const int64_t* hot_ptr, int64_t hot_val, int skip_hot, unsigned* table,
                          unsigned* cnt, int* status, cudaStream_t st);
 int uem_i64_max_accumulate(const int64_t* x, int64_t n, int64_t* out_max, cudaStream_t st);
+int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* index, int b, int64_t N, int c, int64_t R,
+                       unsigned* table, int64_t* maxid_out, int* status, float* tail_sw, int* tail_done, float temp,
+                       unsigned* zero_words, int n_zero, cudaStream_t st);
+int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw, float cutoff_top,
+                                  float cutoff_low, int64_t ignore_label, int64_t* out, const float* uvem, float* entropy,
+                                  float* weight, int64_t* zero_after, int pdl, cudaStream_t st);
 
 #ifndef UEM_REFINE_MINB
 #define UEM_REFINE_MINB 4   // resident 128-thread CTAs per SM the TMA kernel is compiled for (register cap = 64K/(128*MINB))
@@ -64,20 +71,6 @@ template <int C> struct Lay {
     static constexpr int PC = (C + 1) / 2;    // class pairs for packed fp32x2 math
 };
 
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-#ifdef UEM_NO_MUFU
-    return fmaf(x, x, 1.0f);  // development experiment only: takes the XU pipe out of the picture
-#else
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#endif
-}
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
@@ -106,20 +99,6 @@ struct RefineParams {
     unsigned* stats;        // (b, C+2) ordered-u32: per-class max of `out`, -(min of out), bad flag; atomically raised
 };
 
-// e_c = exp(z_c - max z) (one MUFU each; results below 2^-126 flush to 0, irrelevant for a softmax numerator),
-// returns S = sum e_c
-template <int C> __device__ __forceinline__ float exp_shifted(float (&z)[C]) {
-    float mx = z[0];
-#pragma unroll
-    for (int i = 1; i < C; ++i) mx = fmaxf(mx, z[i]);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-        z[i] = ex2_approx((z[i] - mx) * 1.4426950408889634f);
-        s += z[i];
-    }
-    return s;
-}
 // packed variant over PC class pairs
 template <int PC> __device__ __forceinline__ float exp_shifted2(float2 (&z)[PC]) {
     float mx = fmaxf(z[0].x, z[0].y);
@@ -556,9 +535,8 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
     __syncthreads();  // barriers initialised
     int bi = (int)(R0 / H), y = (int)(R0 - (int64_t)bi * H);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE && s < nrows; ++s) issue_row(R0 + s, s);
+        for (int s = 0; s < NSTAGE && s < nrows; ++s) issue_row(R0 + s, s);  // inputs only: safe before the dependency wait
     }
-    fetch_lowres(bi, y);
     // padded class slots: -1e30 -> EX2 gives exactly 0, never wins a max (written once, both tap rows)
     if constexpr (CP > C) {
         for (int i = threadIdx.x; i < 2 * (w + 2) * 3 * (CP - C); i += NT) {
@@ -570,6 +548,14 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
 #if !UEM_XTAB_GLOBAL
     for (int g = threadIdx.x; g < groups; g += NT) xtab_entry<C>(xtab + 4 * g, g, w, p.sx);
 #endif
+    // programmatic dependent launch: everything above touched only this kernel's inputs and its own shared memory;
+    // the similarity map, the region weights and the ignored id are produced by the preceding kernels
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    fetch_lowres(bi, y);
+    const int64_t ignored_id = *p.ignored_id;
+    // ids that take the all-ones sentinel row R: the ignored id (alignment.py:255) and anything outside [0,R)
+    const uint32_t ign_lo = ((uint64_t)ignored_id >> 32) == 0 ? (uint32_t)ignored_id : 0xffffffffu;
     lerp_lowres(rowbuf, y);
     __syncthreads();
 
@@ -658,15 +644,15 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
                 }
             }
 #endif
-            // superpixel view: multiplicative outside the ignored id (branch-free: its table row is all ones; an id
-            // outside [0,R) is redirected to the all-ones sentinel row R)
+            // superpixel view: multiplicative outside the ignored id (branch-free: the ignored id and any id outside
+            // [0,R) are redirected to the all-ones sentinel row R)
             {
                 const longlong2 i01 = ids_s[2 * g], i23 = ids_s[2 * g + 1];
                 const int64_t rid[4] = {i01.x, i01.y, i23.x, i23.y};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t lo = (uint32_t)rid[i], hi = (uint32_t)((uint64_t)rid[i] >> 32);
-                    const uint32_t r = (hi == 0u && lo < Ru) ? lo : Ru;
+                    const uint32_t r = (hi == 0u && lo < Ru && lo != ign_lo) ? lo : Ru;
                     const float4* wp = swb + (size_t)r * (CP / 4);
 #pragma unroll
                     for (int q = 0; q < CP / 4; ++q) {
@@ -720,8 +706,8 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
 }
 
 // superpixel-view weight of every (image, region): softmax(region_max/temp) / (max + 1e-7)  (alignment.py:252-253)
-// table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R+1,CP); the row of the ignored id and
-// row R (the sentinel out-of-range ids are redirected to) are all ones
+// table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R+1,CP); row R (the sentinel the ignored
+// id and out-of-range ids are redirected to) is all ones.  On the fused chain the region-max kernel does this itself.
 template <int C>
 __global__ void __launch_bounds__(256) region_weight_kernel(const void* __restrict__ table, int encoded, int b, int64_t R,
                                                             const int64_t* __restrict__ ignored_ptr, float temp, float inv_temp,
@@ -731,11 +717,11 @@ __global__ void __launch_bounds__(256) region_weight_kernel(const void* __restri
     if (xtab)  // horizontal-weight table of the TMA refine kernel (depends on the column only)
         for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) xtab_entry<C>(xtab + 4 * g, g, w, sx);
     const int64_t rows = (int64_t)b * (R + 1);
-    const int64_t ignored = *ignored_ptr;  // the batch-global max id: weight 1 (alignment.py:255 leaves those pixels alone)
+    (void)ignored_ptr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t bi = i / (R + 1), rl = i - bi * (R + 1);
         float4* dst = reinterpret_cast<float4*>(sw + i * CP);
-        if (rl == R || rl == ignored) {
+        if (rl == R) {
 #pragma unroll
             for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(1.f, 1.f, 1.f, 1.f);
             continue;
@@ -804,22 +790,38 @@ static int sm_count() {
     return n;
 }
 
+// pdl: launch with programmatic stream serialization (the kernel must execute griddepcontrol.wait before it touches
+// anything the preceding kernel of the stream writes)
 template <typename K>
-static int launch_persistent(K kernel, const RefineParams& p, int threads, size_t smem, cudaStream_t st) {
+static int launch_persistent(K kernel, const RefineParams& p, int threads, size_t smem, cudaStream_t st, bool pdl = false) {
     if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t total_rows = (int64_t)p.b * p.H;
     const int grid = (int)min(total_rows, (int64_t)sm_count() * per_sm);
-    kernel<<<grid, threads, smem, st>>>(p);
+    if (!pdl) {
+        kernel<<<grid, threads, smem, st>>>(p);
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
     return 0;
 }
 
 // TMA-fed kernel: NT = 128 threads for rows up to 512 pixels, 256 beyond (a row is one pass of the CTA);
 // two rows in flight per CTA unless a third fits without costing a resident CTA
 template <int C>
-static int launch_refine_tma(RefineParams p, cudaStream_t st, bool* done) {
+static int launch_refine_tma(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
     *done = false;
     const int groups = p.W / 4;
     const int nt = groups > 128 ? 256 : 128;
@@ -837,9 +839,11 @@ static int launch_refine_tma(RefineParams p, cudaStream_t st, bool* done) {
 #endif
     int rc;
     if (nt == 128) {
-        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 128>, p, 128, s3, st) : launch_persistent(refine_tma_kernel<C, 2, 128>, p, 128, s2, st);
+        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 128>, p, 128, s3, st, pdl)
+                   : launch_persistent(refine_tma_kernel<C, 2, 128>, p, 128, s2, st, pdl);
     } else {
-        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 256>, p, 256, s3, st) : launch_persistent(refine_tma_kernel<C, 2, 256>, p, 256, s2, st);
+        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 256>, p, 256, s3, st, pdl)
+                   : launch_persistent(refine_tma_kernel<C, 2, 256>, p, 256, s2, st, pdl);
     }
     *done = (rc == 0);
     return rc;
@@ -848,7 +852,10 @@ static int launch_refine_tma(RefineParams p, cudaStream_t st, bool* done) {
 // sw_ws: b*(R+1)*CP floats of scratch for the per-region weights (superpixel view only)
 static int launch_refine(int views, const float* simi, const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                          const void* table, int table_encoded, int64_t R, const int64_t* ignored_id, const float* soft, int b,
-                         int c, int H, int W, float temp, float* out, unsigned* stats, float* sw_ws, cudaStream_t st) {
+                         int c, int H, int W, float temp, float* out, unsigned* stats, float* sw_ws, cudaStream_t st,
+                         bool weights_ready = false, bool pdl = false) {
+    // weights_ready: sw_ws already holds the per-region weights (fused tail of the region-max kernel); pdl: that kernel
+    // directly precedes this launch in the stream, so the TMA kernel may overlap its prologue with it
     UEM_REQUIRE(soft && out && b > 0 && H > 0 && W > 0, "uem_label_refine_f32: bad arguments");
     UEM_REQUIRE(views > 0 && views < 8, "uem_label_refine_f32: views must be a non-empty mask of UEM_VIEW_*");
     UEM_REQUIRE(temp > 0.f, "uem_label_refine_f32: temp must be > 0");  // alignment.py:313
@@ -886,7 +893,7 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     void *ev0 = nullptr, *ev1 = nullptr;
     int launched = 1, rc = 0;
     UEM_DISPATCH_C(c, {
-        if (views & UEM_VIEW_SUP) {
+        if ((views & UEM_VIEW_SUP) && !weights_ready) {
             const int64_t rows = (int64_t)b * (R + 1);
             region_weight_kernel<C><<<(int)min((int64_t)UEM_SMS * 4, (rows + 255) / 256), 256, 0, st>>>(
                 table, table_encoded, b, R, ignored_id, temp, 1.0f / temp, p.div_temp, sw_ws,
@@ -896,7 +903,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
         bool done = false;
-        if (fast) rc = launch_refine_tma<C>(p, st, &done);
+        static const bool pdl_enabled = !(getenv("UEM_PDL") && getenv("UEM_PDL")[0] == '0');  // development switch
+        if (fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0 && pdl_enabled, &done);
         if (!done && rc == 0) {
             const int vecw = vec ? 4 : 1;
             const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
@@ -955,7 +963,7 @@ extern "C" int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, cons
 //            region   u32[b*R*c]   ordered-encoded region maxima
 // ------------------------------------------------------------------------------------------------
 struct MineLayout {
-    int64_t simi, pearson, sw, zero_begin, maxid, stats, region, end;
+    int64_t simi, pearson, sw, zero_begin, maxid, done, stats, region, end;
 };
 static MineLayout mine_layout(int b, int c, int W, int h, int w, int k, int64_t R) {
     MineLayout L;
@@ -965,6 +973,7 @@ static MineLayout mine_layout(int b, int c, int W, int h, int w, int k, int64_t 
     L.sw = n; n += uem_label_refine_ws_bytes(b, c, R, W);
     L.zero_begin = n;
     L.maxid = n; n += 16;
+    L.done = n; n += align16((int64_t)b * 4);
     L.stats = n; n += uem_class_stats_bytes(b, c);
     L.region = n; n += align16((int64_t)b * R * c * 4);
     L.end = n;
@@ -979,6 +988,32 @@ extern "C" int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, i
     (void)H;
     return mine_layout(b, c, W, h, w, k, R).stats;
 }
+
+// Side stream of the fused chain: the feature-map pass (Pearson similarity) and the soft/superpixel pass (region
+// maxima) are independent until the refine kernel, so they are forked onto two streams and joined with events
+// (capturable: inside a CUDA graph they become two parallel branches).  One set per host thread and device.
+namespace {
+struct SideStream {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+int side_stream(SideStream** out) {
+    static thread_local SideStream side[16];
+    int dev = 0;
+    UEM_CUDA(cudaGetDevice(&dev));
+    UEM_REQUIRE(dev >= 0 && dev < 16, "uem_mine_refine_select_f32: device index %d out of range", dev);
+    SideStream& s = side[dev];
+    if (s.device != dev) {
+        UEM_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        UEM_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        UEM_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        s.device = dev;
+    }
+    *out = &s;
+    return 0;
+}
+}  // namespace
 
 extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos, const float* pred1,
                                           const float* pred2, int h, int w, const int64_t* sup, int64_t R,
@@ -999,34 +1034,63 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     unsigned* table = (unsigned*)(base + L.region);
     const int64_t HW = (int64_t)H * W;
     int rc;
-    UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.end - L.zero_begin), st));
-    // order matters for L2: the feature pass runs first so that soft/sup, read by the region-max pass, are
-    // still L2 resident when the refine kernel reads them again
+    // Self-cleaning fast path (superpixel view, region table fits shared memory): ws is zero on entry (zero-initialised
+    // by the allocator, then kept clean by every call) -- the region-max kernel clears the class statistics, its tail
+    // zeroes the table rows and arrival counters again, the selection kernel zeroes the max-id slot -- so no memset
+    // node sits on the critical path.  Every other configuration zeroes the region before and after the call.
+    const bool selfclean = (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)c * 4 + 1) + 64 <= 200 * 1024;
+    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.end - L.zero_begin), st));
+    // fork: the feature pass runs on the side stream while the region-max pass (below) runs on the caller's stream
+    SideStream* side = nullptr;
+    const bool fork = (views & UEM_VIEW_PROTO) && (views & UEM_VIEW_SUP);
     if (views & UEM_VIEW_PROTO) {
         UEM_REQUIRE(feat && protos, "uem_mine_refine_select_f32: prototype view needs feat and prototypes");
-        if ((rc = uem_pearson_dist_nchw_f32(feat, b, k, (int64_t)h * w, protos, c, eps, 1, simi, pws, stream))) return rc;
+        void* pst = stream;
+        if (fork) {
+            if ((rc = side_stream(&side))) return rc;
+            UEM_CUDA(cudaEventRecord(side->fork, st));
+            UEM_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            pst = (void*)side->stream;
+        }
+        if ((rc = uem_pearson_dist_nchw_f32(feat, b, k, (int64_t)h * w, protos, c, eps, 1, simi, pws, pst))) return rc;
+        if (fork) UEM_CUDA(cudaEventRecord(side->join, side->stream));
     }
+    bool own_maxid = false;
     if (views & UEM_VIEW_SUP) {
         UEM_REQUIRE(sup && R > 0, "uem_mine_refine_select_f32: superpixel view needs sup and a region capacity R");
-        if (!ignored_id) {
-            if ((rc = uem_i64_max_accumulate(sup, (int64_t)b * HW, maxid, st))) return rc;
-            ignored_id = maxid;
+        own_maxid = (ignored_id == nullptr);
+        // region maxima of soft, NCHW viewed as (b,N,c): class stride HW; the batch max id (alignment.py:241) comes out
+        // of the same pass when the caller did not supply it
+        if (selfclean) {
+            if ((rc = uem_region_max_f32(soft, (int64_t)c * HW, HW, sup, b, HW, c, R, table, own_maxid ? maxid : nullptr, status, sw,
+                                         (int*)(base + L.done), temp, stats, b * (c + 2), st)))
+                return rc;
+            if (own_maxid) ignored_id = maxid;
+        } else {
+            if (own_maxid) {
+                if ((rc = uem_i64_max_accumulate(sup, (int64_t)b * HW, maxid, st))) return rc;
+                ignored_id = maxid;
+            }
+            if ((rc = uem_region_table_f32(soft, (int64_t)c * HW, 1, HW, sup, b, HW, c, R, UEM_REDUCE_MAX, ignored_id, -1, 1, table,
+                                           nullptr, status, st)))
+                return rc;
         }
-        // region maxima of soft, NCHW viewed as (b,N,c): strides {c*N, 1, N}; the ignored id is never gathered
-        // (alignment.py:255), so its pixels are skipped
-        if ((rc = uem_region_table_f32(soft, (int64_t)c * HW, 1, HW, sup, b, HW, c, R, UEM_REDUCE_MAX, ignored_id, -1, 1, table,
-                                       nullptr, status, st)))
-            return rc;
     }
+    // join before the refine kernel reads simi; an event wait is a full dependency, so the programmatic overlap with
+    // the region-max kernel is only requested when nothing else sits between the two launches
+    if (fork) UEM_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     if ((rc = launch_refine(views, simi, pred1, pred2, h, w, sup, table, 1, R, ignored_id, soft, b, c, H, W, temp, refined,
-                            stats, sw, st)))
+                            stats, sw, st, selfclean, selfclean)))
         return rc;
-    if (hard || entropy || weight) {
+    const bool select = hard || entropy || weight;
+    if (select) {
         UEM_REQUIRE(hard, "uem_mine_refine_select_f32: entropy/weight outputs come with the selection (hard must be given)");
         UEM_REQUIRE(!(weight && !uvem), "uem_mine_refine_select_f32: weight output needs the uvem parameter block");
-        if ((rc = uem_select_entropy_stats_f32(refined, stats, b, c, HW, cutoff_top, cutoff_low, ignore_label, hard, uvem, entropy,
-                                               weight, stream)))
+        if ((rc = uem_select_entropy_stats_impl(refined, stats, b, c, HW, cutoff_top, cutoff_low, ignore_label, hard, uvem, entropy,
+                                                weight, (selfclean && own_maxid) ? maxid : nullptr, 1, st)))
             return rc;
     }
+    if (selfclean && own_maxid && !select) UEM_CUDA(cudaMemsetAsync(maxid, 0, 16, st));
+    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.stats - L.zero_begin), st));  // leave maxid/done clean
     return 0;
 }

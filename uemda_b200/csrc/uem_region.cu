@@ -228,6 +228,152 @@ __global__ void __launch_bounds__(kThreads, 4) region_reduce_f32_kernel(const fl
     }
 }
 
+// ---------------------------------------------------------------- f32 region MAX, shared-memory privatised
+// The hot-path form (region maxima of the soft labels, alignment.py:245): every CTA scans a contiguous pixel range of
+// one image and keeps a private (R, C) table of order-encoded maxima in shared memory.  A thread reduces runs of equal
+// ids in registers; a finished run is merged test-then-atomic (LDS probe, ATOMS.MAX only when the slot would be
+// raised), so the hot "ignored" id costs a probe, not a contended atomic.  Only the regions the CTA touched (byte flags)
+// are merged into the global table, again test-then-atomic (ld.cg probe, RED.MAX only when raising).  The batch-global
+// max id (alignment.py:241) falls out of the same pass (one atomicMax per CTA), which removes the separate pass over
+// the int64 id map.
+// Optional fused tail (RegionTail): the last CTA to finish an image turns that image's maxima into the superpixel-view
+// weights softmax(max/temp)/(max_c + 1e-7) (alignment.py:252-253) and zeroes the table rows again, so the table is
+// clean for the next call and no separate weight kernel / memset sits on the critical path.
+struct RegionTail {
+    float* sw;           // (b, R+1, CP) weights out (row R = all-ones sentinel); null = no tail
+    int* done;           // (b) arrival counters: zero on entry, left zero
+    float temp, inv_temp;
+    int div_temp;
+    unsigned* zero_words;  // cleared by CTA (0,0) on entry (the class-statistics table the refine kernel raises next)
+    int n_zero;
+};
+
+template <int C, int VEC>
+__global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* __restrict__ src, int64_t sb, int64_t sc,
+                                                              const int64_t* __restrict__ index, int64_t N, int64_t R,
+                                                              unsigned* __restrict__ table, long long* __restrict__ maxid,
+                                                              int* __restrict__ status, const RegionTail tail) {
+    constexpr int CP = (C + 3) & ~3;
+    extern __shared__ __align__(16) unsigned tab_s[];  // [R][C] then [R] touched flags
+    __shared__ long long smax[32];
+    __shared__ int s_last;
+    const int bi = blockIdx.y;
+    const float* s = src + (int64_t)bi * sb;
+    const int64_t* idx = index + (int64_t)bi * N;
+    const int RC = (int)(R * C);
+    const int words = (RC + (int)((R + 3) / 4) + 3) & ~3;
+    unsigned char* touched = reinterpret_cast<unsigned char*>(tab_s + RC);
+    // the dependent kernel (refine) may start its own prologue now (programmatic dependent launch)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = threadIdx.x * 4; i < words; i += blockDim.x * 4) *reinterpret_cast<uint4*>(tab_s + i) = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0 && bi == 0)
+        for (int i = threadIdx.x; i < tail.n_zero; i += blockDim.x) tail.zero_words[i] = 0u;
+    __syncthreads();
+
+    const int64_t groups = N / VEC;
+    const int64_t per = (groups + gridDim.x - 1) / gridDim.x;
+    const int64_t g0 = (int64_t)blockIdx.x * per, g1 = min(groups, g0 + per);
+    int cur = -1;
+    float acc[C];
+    long long mx = 0;
+    bool badid = false;
+    auto flush = [&]() {
+        if (cur >= 0) {
+            unsigned* slot = tab_s + cur * C;
+            touched[cur] = 1;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const unsigned e = f32_to_ordered(acc[ci]);
+                if (e > slot[ci]) atomicMax(slot + ci, e);
+            }
+        }
+    };
+    for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+        const int64_t n0 = g * VEC;
+        int64_t id[VEC];
+        load_ids<VEC>(idx + n0, id);
+        float v[C][VEC];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            PixVec<VEC> t;
+            t.load(s + n0 + (int64_t)ci * sc);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[ci][i] = t.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const long long r64 = id[i];
+            if (r64 < 0 || r64 >= R) { badid = true; continue; }
+            mx = max(mx, r64);
+            const int r = (int)r64;
+            if (r != cur) {
+                flush();
+                cur = r;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) acc[ci] = v[ci][i];
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) acc[ci] = fmaxf(acc[ci], v[ci][i]);
+            }
+        }
+    }
+    flush();
+    if (badid && status) atomicOr(status, 2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0 && maxid) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = max(mx, smax[i]);
+        if (mx > 0) atomicMax(maxid, mx);
+    }
+    unsigned* tab = table + (int64_t)bi * R * C;
+    for (int r = threadIdx.x; r < (int)R; r += blockDim.x) {
+        if (!touched[r]) continue;
+        unsigned old[C];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) old[ci] = ld_cg_u32(tab + r * C + ci);
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const unsigned e = tab_s[r * C + ci];
+            if (e > old[ci]) atomicMax(tab + r * C + ci, e);
+        }
+    }
+    if (tail.sw == nullptr) return;
+    // ---- last CTA of this image: per-region weights, table rows back to zero
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + bi, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float* swb = tail.sw + (int64_t)bi * (R + 1) * CP;
+    for (int r = threadIdx.x; r <= (int)R; r += blockDim.x) {
+        float4* dst = reinterpret_cast<float4*>(swb + (int64_t)r * CP);
+        if (r == (int)R) {
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+            continue;
+        }
+        float z[C];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const unsigned e = ld_cg_u32(tab + r * C + ci);
+            const float v = e ? ordered_to_f32(e) : 0.f;  // untouched slots are 0 like torch_scatter's output
+            z[ci] = tail.div_temp ? __fdiv_rn(v, tail.temp) : v * tail.inv_temp;
+            tab[r * C + ci] = 0u;
+        }
+        const float S = exp_shifted<C>(z);
+        const float rs = fmaf(-1e-7f, S, 1.0f);
+        float o[CP];
+#pragma unroll
+        for (int ci = 0; ci < CP; ++ci) o[ci] = ci < C ? z[ci < C ? ci : 0] * rs : 0.f;
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+    if (threadIdx.x == 0) tail.done[bi] = 0;
+}
+
 // decode the slot table into the dense float output torch_scatter returns (untouched -> 0)
 __global__ void region_decode_f32_kernel(const unsigned* __restrict__ table, const unsigned* __restrict__ cnt, int64_t total,
                                          int c, int op, float* __restrict__ out) {
@@ -403,12 +549,53 @@ extern "C" int64_t uem_region_reduce_ws_bytes(int b, int64_t R, int c) {
     return ((int64_t)b * R * c + (int64_t)b * R + 4) * 4;
 }
 
+// Region maxima of a planar map into the encoded table (zero on entry); optionally the batch max id (maxid_out zero on
+// entry, ids are >= 0) and the fused weight tail (see RegionTail; tail_sw == nullptr: plain reduction).
+// Needs R*c*4 + R bytes of shared memory per CTA.
+int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* index, int b, int64_t N, int c, int64_t R,
+                       unsigned* table, int64_t* maxid_out, int* status, float* tail_sw, int* tail_done, float temp,
+                       unsigned* zero_words, int n_zero, cudaStream_t st) {
+    const bool vec = (N % 4 == 0) && (sb % 4 == 0) && (sc % 4 == 0) && uem_aligned16(src) && uem_aligned16(index);
+    const size_t smem = ((size_t)R * c * 4 + (size_t)((R + 3) / 4) * 4 + 15) & ~(size_t)15;
+    UEM_REQUIRE(smem <= 200 * 1024, "uem_region_max_f32: region table (%lld x %d) exceeds shared memory", (long long)R, c);
+    // the kernel is compiled for <= 64 registers (1024 threads per SM): two CTAs of 512 threads per SM when two private
+    // tables fit, otherwise a single 1024-thread CTA; one wave
+    const int threads = (2 * (smem + 1024) <= 220 * 1024) ? 512 : 1024;
+    const int per_sm = threads == 512 ? 2 : 1;
+    int chunks = max(1, (UEM_SMS * per_sm) / b);
+    const int64_t groups = N / (vec ? 4 : 1);
+    chunks = (int)min((int64_t)chunks, max((int64_t)1, groups / threads));
+    RegionTail tail{};
+    tail.sw = tail_sw;
+    tail.done = tail_done;
+    tail.temp = temp;
+    tail.inv_temp = 1.0f / temp;
+    int ex;
+    tail.div_temp = (frexpf(temp, &ex) == 0.5f) ? 0 : 1;
+    tail.zero_words = zero_words;
+    tail.n_zero = zero_words ? n_zero : 0;
+    UEM_DISPATCH_C(c, {
+        dim3 grid(chunks, b);
+        if (vec) {
+            if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            region_max_smem_kernel<C, 4><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail);
+        } else {
+            if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            region_max_smem_kernel<C, 1><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail);
+        }
+    });
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
 // Internal entry shared with the fused refine path (uem_refine.cu): fills the encoded slot table only.
 int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, const int64_t* index, int b, int64_t N,
                          int c, int64_t R, int op, const int64_t* hot_ptr, int64_t hot_val, int skip_hot, unsigned* table,
                          unsigned* cnt, int* status, cudaStream_t st) {
     const int kop = (op == UEM_REDUCE_MAX) ? UEM_REDUCE_MAX : UEM_REDUCE_SUM;
     const bool vec = (sn == 1) && (N % 4 == 0) && (sb % 4 == 0) && (sc % 4 == 0) && uem_aligned16(src) && uem_aligned16(index);
+    if (kop == UEM_REDUCE_MAX && !cnt && sn == 1 && R * (c * 4 + 1) + 64 <= 200 * 1024)
+        return uem_region_max_f32(src, sb, sc, index, b, N, c, R, table, nullptr, status, nullptr, nullptr, 1.0f, nullptr, 0, st);
     UEM_DISPATCH_C(c, {
         if (vec) {
             dim3 grid(uem_div_up(N / 4, kThreads * kSteps), b);

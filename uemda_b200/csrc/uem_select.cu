@@ -6,6 +6,10 @@
 // class plane, class vector in registers, thresholds in shared memory.
 #include "uem_common.cuh"
 
+int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw, float cutoff_top,
+                                  float cutoff_low, int64_t ignore_label, int64_t* out, const float* uvem, float* entropy,
+                                  float* weight, int64_t* zero_after, int pdl, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -156,9 +160,12 @@ __global__ void __launch_bounds__(kThreads) select_stats_kernel(const float* __r
                                                                 int64_t hw, float top, float low, int64_t ignore_label,
                                                                 int64_t* __restrict__ out, int has_uvem, float um, float ut,
                                                                 float uig, float ucl, float ucr, float* __restrict__ entropy,
-                                                                float* __restrict__ weight) {
+                                                                float* __restrict__ weight, int64_t* __restrict__ zero_after) {
     __shared__ float thr[C];
     const int bi = blockIdx.y;
+    // programmatic dependent launch: the CTAs may already be resident while the refine kernel drains
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (zero_after && blockIdx.x == 0 && bi == 0 && threadIdx.x == 0) zero_after[0] = 0;  // max-id slot of the fused chain: clean for the next call
     thresholds_from_stats<C>(stats, bi, top, low, thr);
     const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (g * VEC >= hw) return;
@@ -219,34 +226,62 @@ __global__ void class_stats_decode_kernel(const unsigned* __restrict__ stats, in
 extern "C" int uem_select_entropy_stats_f32(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw,
                                             float cutoff_top, float cutoff_low, int64_t ignore_label, int64_t* out,
                                             const float* uvem, float* entropy, float* weight, void* stream) {
+    return uem_select_entropy_stats_impl(mask, class_stats, b, c, hw, cutoff_top, cutoff_low, ignore_label, out, uvem, entropy, weight,
+                                         nullptr, 0, (cudaStream_t)stream);
+}
+
+namespace {
+template <typename K, typename... Args>
+int launch_maybe_pdl(K kernel, dim3 grid, int threads, cudaStream_t st, int pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    UEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+    return 0;
+}
+}  // namespace
+
+// zero_after: optional int64 slot cleared by the kernel (fused chain housekeeping); pdl: launch with programmatic
+// stream serialization (the kernel waits for the preceding kernel itself, its launch latency overlaps that kernel)
+int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw, float cutoff_top,
+                                  float cutoff_low, int64_t ignore_label, int64_t* out, const float* uvem, float* entropy,
+                                  float* weight, int64_t* zero_after, int pdl, cudaStream_t st) {
     UEM_REQUIRE(mask && class_stats && out && b > 0 && hw > 0, "uem_select_entropy_stats_f32: bad arguments");
     UEM_REQUIRE(!(weight && !uvem), "uem_select_entropy_stats_f32: weight output needs the uvem parameter block");
-    cudaStream_t st = (cudaStream_t)stream;
     const bool vec = uem_aligned16(mask) && uem_aligned16(out) && (hw % 4 == 0) && (!entropy || uem_aligned16(entropy)) &&
                      (!weight || uem_aligned16(weight));
     const int hu = uvem ? 1 : 0;
     const float um = hu ? uvem[0] : 0.f, ut = hu ? uvem[1] : 1.f, uig = hu ? uvem[2] : 1.f, ucl = hu ? uvem[3] : 0.f,
                 ucr = hu ? uvem[4] : 0.f;
     const bool extra = entropy || weight;
+    const unsigned* stats = class_stats;
+    int rc = 0;
     UEM_DISPATCH_C(c, {
         if (vec) {
             dim3 grid(uem_div_up(hw / 4, kThreads), b);
             if (extra)
-                select_stats_kernel<C, 4, true><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
-                                                                           out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+                rc = launch_maybe_pdl(select_stats_kernel<C, 4, true>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
             else
-                select_stats_kernel<C, 4, false><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
-                                                                            out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+                rc = launch_maybe_pdl(select_stats_kernel<C, 4, false>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
         } else {
             dim3 grid(uem_div_up(hw, kThreads), b);
             if (extra)
-                select_stats_kernel<C, 1, true><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
-                                                                           out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+                rc = launch_maybe_pdl(select_stats_kernel<C, 1, true>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
             else
-                select_stats_kernel<C, 1, false><<<grid, kThreads, 0, st>>>(mask, class_stats, hw, cutoff_top, cutoff_low, ignore_label,
-                                                                            out, hu, um, ut, uig, ucl, ucr, entropy, weight);
+                rc = launch_maybe_pdl(select_stats_kernel<C, 1, false>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
         }
     });
+    if (rc) return rc;
     UEM_CHECK_LAUNCH();
     return 0;
 }

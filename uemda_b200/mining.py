@@ -60,8 +60,8 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
             R = int(num_regions)
     need = lib.uem_mine_ws_bytes(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
     if ws is None or ws.numel() < need:
-        ws = L.workspace(need, soft)
-        ws[:32].zero_()
+        # the chain keeps its scratch self-cleaning: it must be zero the first time (include/uem_b200.h)
+        ws = torch.zeros(max(int(need), 16), dtype=torch.uint8, device=soft.device)
     refined = torch.empty_like(soft)
     hard = None
     top = low = 0.0
