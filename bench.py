@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner to stdout at WARN/VERSION level: keep stdout to the JSON line
+
 import torch  # noqa: E402
 
 UVEM = (0.2, 0.7, 4.0)      # --uvem-m/-t/-g, tools/train_ssl_uem.py:59-61
@@ -230,27 +232,60 @@ def main():
     ws = None
 
     side = torch.cuda.Stream(device=dev)
+    proto_state = al.prototypes.clone()   # the replicated prototype bank: read by the refine chain, EMA-updated in place
+    al.prototypes = proto_state
+    n_pack = wl.c * wl.k + wl.c + 1
+    # one exchange buffer pair per input set: phase A + all_gather of step i+1 run one step ahead of phase B of step i
+    packed_bufs = [torch.zeros(n_pack, dtype=torch.float64, device=dev) for _ in range(args.sets)]
+    gathered_bufs = [torch.zeros((world, n_pack), dtype=torch.float64, device=dev) for _ in range(args.sets)]
+    ahead = torch.cuda.Stream(device=dev)
+    ev_a = [torch.cuda.Event() for _ in range(args.sets)]
+    ev_b = [torch.cuda.Event() for _ in range(args.sets)]
 
-    def step_resident(s):
-        """device-resident step, no host sync (strict asserts off).  The source-side chain (DownscaleLabel ->
-        masked prototype sums -> EMA) is independent of the target-side chain until the next step, so it runs on a
-        second stream; the EMA result is only published after the target chain has read the old prototypes."""
-        nonlocal ws
+    def source_stats(s):
+        """source-side chain on the second stream: DownscaleLabel -> masked prototype sums (independent of the target chain)"""
         cur = torch.cuda.current_stream(dev)
-        protos = al.prototypes
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            if miner:
-                miner.update_prototype(s["feat_s"], s["label_s"])
-            else:
-                al.update_prototype(s["feat_s"], s["label_s"])
-        ignored = miner.global_ignored_id(s["sup"]) if miner else None
-        refined, hard, ent, wgt = mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=protos,
-                                                       pred1=s["pred1"], pred2=s["pred2"], sup=s["sup"], num_regions=R,
-                                                       ignored_id=ignored, eps=al.eps, select=(CUTOFF[0], CUTOFF[1], -1),
-                                                       ws=ws, uvem=UVEM)
+            down = al.downscale_gt(s["label_s"])
+            sums, counts = ops.proto_accumulate(s["feat_s"], down, wl.c, -1)
+        return sums, counts
+
+    def target_chain(s, ignored):
+        return mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=proto_state, pred1=s["pred1"],
+                                    pred2=s["pred2"], sup=s["sup"], num_regions=R, ignored_id=ignored, eps=al.eps,
+                                    select=(CUTOFF[0], CUTOFF[1], -1), ws=ws, uvem=UVEM)
+
+    def step_resident(s):
+        """device-resident single-GPU step, no host sync (strict asserts off): source chain and target chain on two
+        streams; the EMA writes the prototype bank in place once the target chain (its last reader) is enqueued."""
+        nonlocal ws
+        cur = torch.cuda.current_stream(dev)
+        sums, counts = source_stats(s)
+        out = target_chain(s, None)
         cur.wait_stream(side)
-        return refined, hard, ent, wgt
+        ops.proto_finalize(sums, counts, proto_state, eps=al.eps, decay=DECAY, want_local=False, out=proto_state)
+        return out
+
+    # multi-GPU: the batch is sharded by image; the only exchange is ONE all_gather of [prototype sums | counts | max id]
+    # per step, kept outside the captured graphs (phase A: local statistics; phase B: fold + target chain + EMA)
+    def phase_a(s, j):
+        cur = torch.cuda.current_stream(dev)
+        sums, counts = source_stats(s)
+        mx = ops.i64_minmax(s["sup"])[1:]
+        cur.wait_stream(side)
+        packed_bufs[j].copy_(mining.pack_local(sums, counts, mx))
+
+    def phase_b(s, j):
+        sums, counts, ignored = miner.fold(gathered_bufs[j])
+        out = target_chain(s, ignored)
+        ops.proto_finalize(sums, counts, proto_state, eps=al.eps, decay=DECAY, want_local=False, out=proto_state)
+        return out
+
+    def step_sharded(s, j=0):
+        phase_a(s, j)
+        miner.exchange(packed_bufs[j], out=gathered_bufs[j])
+        return phase_b(s, j)
 
     def barrier():
         if world > 1:
@@ -260,23 +295,31 @@ def main():
     config.strict_asserts = False
     need = lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, R)
     ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+    step_eager = step_sharded if miner else step_resident
 
-    # ---- warm-up (eager), then graph capture: one graph per buffer set
+    # ---- warm-up (eager), then graph capture: one graph (two around the exchange when sharded) per buffer set
     for i in range(max(args.warmup, 3)):
-        step_resident(sets[i % args.sets])
+        step_eager(sets[i % args.sets])
     barrier()
     graphs = None
     if not args.no_graph:
         try:
             graphs = []
             keep = []
-            for s in sets:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    keep.append(step_resident(s))
-                graphs.append(g)
-            for g in graphs:
-                g.replay()
+            for j, s in enumerate(sets):
+                if miner:
+                    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga):
+                        phase_a(s, j)
+                    miner.exchange(packed_bufs[j], out=gathered_bufs[j])
+                    with torch.cuda.graph(gb):
+                        keep.append(phase_b(s, j))
+                    graphs.append((ga, gb))
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        keep.append(step_resident(s))
+                    graphs.append(g)
             barrier()
         except Exception as e:  # noqa: BLE001
             if rank == 0:
@@ -284,21 +327,43 @@ def main():
             graphs = None
             torch.cuda.synchronize()
 
-    def run_step(i):
-        if graphs is not None:
-            graphs[i % args.sets].replay()
-        else:
-            step_resident(sets[i % args.sets])
+    def issue_ahead(i):
+        """phase A + the all_gather of step i on the look-ahead stream"""
+        j = i % args.sets
+        with torch.cuda.stream(ahead):
+            ahead.wait_event(ev_b[j])       # phase B that last read this buffer pair has finished
+            graphs[j][0].replay()
+            miner.exchange(packed_bufs[j], out=gathered_bufs[j])
+            ev_a[j].record(ahead)
 
-    for i in range(args.warmup):
-        run_step(i)
+    def run_steps(first, n):
+        cur = torch.cuda.current_stream(dev)
+        if graphs is None:
+            for i in range(first, first + n):
+                step_eager(sets[i % args.sets])
+        elif miner:
+            for e in ev_b:
+                e.record(cur)
+            issue_ahead(first)
+            for i in range(first, first + n):
+                if i + 1 < first + n:
+                    issue_ahead(i + 1)
+                j = i % args.sets
+                cur.wait_event(ev_a[j])
+                graphs[j][1].replay()
+                ev_b[j].record(cur)
+        else:
+            for i in range(first, first + n):
+                graphs[i % args.sets].replay()
+
+
+    run_steps(0, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     launches0 = lib.uem_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        run_step(i)
+    run_steps(args.warmup, args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
@@ -321,7 +386,7 @@ def main():
     l0 = lib.uem_kernel_launches()
     for i in range(n_k):
         lib.uem_profile_refine_events(evs[i][0].cuda_event, evs[i][1].cuda_event)
-        step_resident(sets[i % args.sets])
+        step_eager(sets[i % args.sets])
     torch.cuda.synchronize()
     per_step_launches = (lib.uem_kernel_launches() - l0) / max(n_k, 1)
     for a, b2 in evs:
@@ -340,8 +405,24 @@ def main():
         h2d = sum(host[k].numel() * host[k].element_size() for k in host)
         d2h = hard_host.numel() * hard_host.element_size()
 
-        def step_e2e():
-            d = {k: host[k].to(dev, non_blocking=True) for k in host}
+        # double-buffered input staging: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i; every
+        # step still pays its own full H2D of all inputs and D2H of the hard labels inside the timed region
+        copy_stream = torch.cuda.Stream(device=dev)
+        dbuf = [{k: torch.empty_like(host[k], device=dev) for k in host} for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_copy(j):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[j % 2])
+                for k in host:
+                    dbuf[j % 2][k].copy_(host[k], non_blocking=True)
+                copied[j % 2].record(copy_stream)
+
+        def compute(j):
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(copied[j % 2])
+            d = dbuf[j % 2]
             refined = al.label_refine(d["sup"], d["feat"], [d["pred1"], d["pred2"]], d["soft"], refine=True, mode="all", temp=TEMP)
             hard = pseudo_selection(refined, CUTOFF[0], CUTOFF[1], "tensor", -1)
             if miner:
@@ -349,16 +430,24 @@ def main():
             else:
                 al.update_prototype(d["feat_s"], d["label_s"])
             ops.entropy_uvem_weight(refined, *UVEM)
+            consumed[j % 2].record(cur)
             hard_host.copy_(hard, non_blocking=True)
 
+        def run_e2e(n):
+            for e in consumed:
+                e.record(torch.cuda.current_stream(dev))
+            issue_copy(0)
+            for j in range(n):
+                if j + 1 < n:
+                    issue_copy(j + 1)
+                compute(j)
+
         n_e = max(3, min(args.steps, 30))
-        for _ in range(3):
-            step_e2e()
+        run_e2e(3)
         barrier()
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(n_e):
-            step_e2e()
+        run_e2e(n_e)
         b2.record()
         barrier()
         e_ms = a.elapsed_time(b2) / n_e
@@ -368,7 +457,8 @@ def main():
         e_ms = float(te.item())
         e2e = {"value": world * wl.pixels / e_ms / 1e3, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "steps": n_e,
-               "api": "Aligner.label_refine + pseudo_selection + Aligner.update_prototype + entropy/UVEM weight"}
+               "api": "Aligner.label_refine + pseudo_selection + Aligner.update_prototype + entropy/UVEM weight",
+               "staging": "pinned host inputs, double-buffered: H2D of step i+1 overlaps the kernels of step i"}
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:

@@ -127,7 +127,7 @@ def test_synth_is_deterministic():
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["UEM_ROOT"])
-from uemda_b200.mining import pack_stats, unpack_stats, shard_range
+from uemda_b200.mining import pack_stats, unpack_stats, shard_range, pack_local, fold_gathered
 from oracle import uem_oracle as O
 from uemda_b200.synth import Workload, make_inputs
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -150,6 +150,13 @@ assert torch.allclose(S, s_all, rtol=1e-5, atol=1e-5)
 assert torch.equal(N, n_all.reshape(-1).long())
 assert torch.equal(Hh[:-1], h_all) and int(Hh[-1]) == int(v_all)
 assert int(mx) == int(inp["sup"].max())
+# the three-phase form: one all_gather of [sums | counts | max id], folded in rank order on every rank
+packed = pack_local(s, n.reshape(-1).long(), inp["sup"][lo:hi].max().reshape(1))
+gathered = torch.empty(world, packed.numel(), dtype=torch.float64)
+dist.all_gather_into_tensor(gathered.reshape(-1), packed)
+S2, N2, M2 = fold_gathered(gathered, wl.c, wl.k)
+assert torch.allclose(S2, s_all, rtol=1e-5, atol=1e-5) and torch.equal(N2, n_all.reshape(-1).long())
+assert int(M2) == int(inp["sup"].max())
 # sharded refine with the GLOBAL ignored id == un-sharded refine (alignment.py:241 is batch-global)
 full = O.label_refine(inp["sup"], inp["feat"], [inp["pred1"], inp["pred2"]], inp["soft"], inp["prototypes"])
 sup_l = inp["sup"][lo:hi].clone()

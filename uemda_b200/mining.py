@@ -125,9 +125,32 @@ def unpack_stats(buf, c, k, with_hist):
     return sums, counts, hist
 
 
+def pack_local(sums, counts, max_id):
+    """[c*k sums | c counts | max superpixel id] as one fp64 vector: the rank-local statistics of one step.
+    Every part is exact in fp64 (fp32 sums, integer counts and ids < 2^53)."""
+    return torch.cat([sums.reshape(-1).double(), counts.reshape(-1).double(), max_id.reshape(-1)[:1].double()])
+
+
+def fold_gathered(gathered, c, k):
+    """(world, c*k+c+1) all-gathered rank vectors -> (sums (c,k) fp32, counts (c,) int64, global max id (1,) int64).
+    The sum runs over ranks in rank order on every rank, so all ranks get bit-identical prototypes."""
+    tot = gathered[0].clone()
+    for r in range(1, gathered.shape[0]):
+        tot[:c * k + c] += gathered[r, :c * k + c]
+    sums = tot[:c * k].float().reshape(c, k)
+    counts = tot[c * k:c * k + c].round().long()
+    max_id = gathered[:, c * k + c].max().round().long().reshape(1)
+    return sums, counts, max_id
+
+
 class ShardedMiner:
     """Runs the mining step on this rank's shard of a global batch and keeps the replicated state
-    (prototype bank, class-frequency EMA) identical on every rank."""
+    (prototype bank, class-frequency EMA) identical on every rank.
+
+    Two ways to drive it:
+      * eager: ``mine`` / ``update_prototype`` (all_reduce per exchange);
+      * three-phase, for CUDA-graph replay with the collective kept OUTSIDE the captured regions:
+        ``local_stats`` (capturable) -> ``exchange`` (one all_gather of <= 100 KB, eager) -> ``apply`` (capturable)."""
 
     def __init__(self, aligner, group=None):
         import torch.distributed as dist
@@ -136,6 +159,44 @@ class ShardedMiner:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    # ---- three-phase form
+    def local_stats(self, sup_local, feat_s_local, label_s_local, out=None):
+        """Rank-local [prototype sums | counts | max superpixel id] of this step -> fp64 vector (written into ``out``
+        when given).  Also returns the down-scaled source labels."""
+        al = self.aligner
+        down = al.downscale_gt(label_s_local)
+        sums, counts = ops.proto_accumulate(feat_s_local, down, al.class_num, al.ignore_label)
+        packed = pack_local(sums, counts, ops.i64_minmax(sup_local)[1:])
+        if out is not None:
+            out.copy_(packed)
+            packed = out
+        return packed, down
+
+    def exchange(self, packed, out=None):
+        """all_gather of the packed rank vectors -> (world, n) fp64."""
+        if out is None:
+            out = torch.empty((self.world, packed.numel()), dtype=packed.dtype, device=packed.device)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out.reshape(-1), packed, group=self.group)
+        else:
+            out[0].copy_(packed)
+        return out
+
+    def fold(self, gathered):
+        """Gathered statistics folded in rank order -> (sums, counts, batch-global ignored id (1,) int64)."""
+        al = self.aligner
+        return fold_gathered(gathered, al.class_num, al.prototypes.shape[1])
+
+    def apply(self, gathered, in_place=False):
+        """fold + EMA update of the prototype bank (alignment.py:347-353); returns the ignored id (alignment.py:241).
+        in_place: write the new bank over the old tensor (only after every reader of the old bank has been enqueued)."""
+        al = self.aligner
+        sums, counts, max_id = self.fold(gathered)
+        _, new = ops.proto_finalize(sums, counts, al.prototypes, eps=al.eps, decay=al.decay, want_local=False,
+                                    out=al.prototypes if in_place else None)
+        al.prototypes = new
+        return max_id
 
     def global_ignored_id(self, sup_local):
         """all_reduce(MAX) of the local max superpixel id -> (1,) int64 device tensor (alignment.py:241)."""

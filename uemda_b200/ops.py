@@ -336,14 +336,15 @@ def proto_accumulate_soft(feat, soft):
     return sums
 
 
-def proto_finalize(sums, counts, proto_old, eps=1e-7, decay=None, mean_n=0, want_local=True):
-    """local = sums/(cnt+eps) with the keep-old rule (or sums/mean_n), optional EMA. Returns (local, new)."""
+def proto_finalize(sums, counts, proto_old, eps=1e-7, decay=None, mean_n=0, want_local=True, out=None):
+    """local = sums/(cnt+eps) with the keep-old rule (or sums/mean_n), optional EMA. Returns (local, new).
+    out: optional (c,k) fp32 tensor receiving the EMA result; may be ``proto_old`` itself (element-wise, in place)."""
     L.require_cuda(sums, counts, proto_old)
     c, k = sums.shape
     lib = L.bind(sums)
     proto_old = L.f32c(proto_old.detach())
     local = torch.empty_like(sums) if want_local else None
-    new = torch.empty_like(sums) if decay is not None else None
+    new = (out if out is not None else torch.empty_like(sums)) if decay is not None else None
     omd, d = (f32(1.0 - decay), f32(decay)) if decay is not None else (0.0, 0.0)
     L.check(lib.uem_proto_finalize_ema_f32(L.ptr(sums), L.ptr(counts), int(mean_n), L.ptr(proto_old), c, k, f32(eps), omd, d,
                                            L.ptr(local), L.ptr(new), L.stream_of(sums)))
