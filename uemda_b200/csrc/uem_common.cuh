@@ -253,20 +253,30 @@ __device__ __forceinline__ float uvem_weight_dev(float u, float m, float t, floa
     return (u >= t) ? 0.f : w;
 }
 
-// entropy sum_c -p log p (balance.py:372).  The cheap log (lg2.approx, 2 ulp for p < 0.5) is used except for the
-// (at most one) class with p >= 0.5, where its 2^-22 absolute error would dominate a small -p log p: that one
-// gets the accurate logf.  p == 0 yields NaN exactly like the reference.
+// entropy sum_c -p log p (balance.py:372) = -ln2 * sum_c p*lg2(p): one MUFU.LG2 + one FFMA per class.
+// lg2.approx is 2 ulp for p < 0.5 but only 2^-22 ABSOLUTE on [0.5, 2), which would dominate the small term of a
+// confident pixel; the (at most one) class with p >= 1 - 2^-6 therefore gets log(p) = log1p(-d), d = 1 - p, from its
+// series (-d - d^2/2 - d^3/3 - d^4/4, truncation < 2e-8 relative), everything branch-free.  Below that bound the other
+// classes carry enough entropy for the absolute error to stay under 1e-5 relative.  p == 0 yields NaN (0 * -inf)
+// exactly like the reference.
 template <int C>
 __device__ __forceinline__ float entropy_px(const float (&p)[C]) {
-    float u = 0.f, vmax = p[0];
+    float t = 0.f, vmax = p[0];
 #pragma unroll
     for (int ci = 0; ci < C; ++ci) {
         const float v = p[ci];
         vmax = fmaxf(vmax, v);
-        u += (-v) * __logf(v);
+        float l;
+        asm("lg2.approx.f32 %0, %1;" : "=f"(l) : "f"(v));
+        t = fmaf(v, l, t);
     }
-    // one accurate log per pixel, control flow uniform across the warp: swap the fast term of the largest
-    // class for the accurate one when it matters (p_max >= 0.5; NaN/zero patterns are untouched)
-    const float fix = (-vmax) * (logf(vmax) - __logf(vmax));
-    return (vmax >= 0.5f) ? u + fix : u;
+    float u = t * -0.69314718055994531f;
+    // swap the approximate term of the dominant class for the series when it is within 2^-6 of 1
+    const float d = 1.0f - vmax;
+    float lm;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(lm) : "f"(vmax));
+    const float approx_term = (vmax * lm) * -0.69314718055994531f;
+    const float series = -d * fmaf(d, fmaf(d, fmaf(d, 0.25f, 0.33333334f), 0.5f), 1.0f);   // log(1 - d)
+    const float exact_term = -vmax * series;
+    return (d < 0.015625f) ? (u - approx_term) + exact_term : u;
 }

@@ -1038,7 +1038,7 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     // by the allocator, then kept clean by every call) -- the region-max kernel clears the class statistics, its tail
     // zeroes the table rows and arrival counters again, the selection kernel zeroes the max-id slot -- so no memset
     // node sits on the critical path.  Every other configuration zeroes the region before and after the call.
-    const bool selfclean = (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)c * 4 + 1) + 64 <= 200 * 1024;
+    const bool selfclean = (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)cp_of(c) * 4 + 1) + 64 <= 200 * 1024;
     if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.end - L.zero_begin), st));
     // fork: the feature pass runs on the side stream while the region-max pass (below) runs on the caller's stream
     SideStream* side = nullptr;

@@ -250,19 +250,19 @@ struct RegionTail {
 
 template <int C, int VEC>
 __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* __restrict__ src, int64_t sb, int64_t sc,
-                                                              const int64_t* __restrict__ index, int64_t N, int64_t R,
-                                                              unsigned* __restrict__ table, long long* __restrict__ maxid,
-                                                              int* __restrict__ status, const RegionTail tail) {
-    constexpr int CP = (C + 3) & ~3;
-    extern __shared__ __align__(16) unsigned tab_s[];  // [R][C] then [R] touched flags
+                                                                 const int64_t* __restrict__ index, int64_t N, int64_t R,
+                                                                 unsigned* __restrict__ table, long long* __restrict__ maxid,
+                                                                 int* __restrict__ status, const RegionTail tail) {
+    constexpr int CP = (C + 3) & ~3;   // private rows are padded to CP words: a probe is CP/4 x LDS.128
+    extern __shared__ __align__(16) unsigned tab_s[];  // [R][CP] then [R] touched flags
     __shared__ long long smax[32];
     __shared__ int s_last;
     const int bi = blockIdx.y;
     const float* s = src + (int64_t)bi * sb;
     const int64_t* idx = index + (int64_t)bi * N;
-    const int RC = (int)(R * C);
-    const int words = (RC + (int)((R + 3) / 4) + 3) & ~3;
-    unsigned char* touched = reinterpret_cast<unsigned char*>(tab_s + RC);
+    const int RP = (int)(R * CP);
+    const int words = (RP + (int)((R + 3) / 4) + 3) & ~3;
+    unsigned char* touched = reinterpret_cast<unsigned char*>(tab_s + RP);
     // the dependent kernel (refine) may start its own prologue now (programmatic dependent launch)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int i = threadIdx.x * 4; i < words; i += blockDim.x * 4) *reinterpret_cast<uint4*>(tab_s + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -273,21 +273,11 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
     const int64_t groups = N / VEC;
     const int64_t per = (groups + gridDim.x - 1) / gridDim.x;
     const int64_t g0 = (int64_t)blockIdx.x * per, g1 = min(groups, g0 + per);
-    int cur = -1;
-    float acc[C];
     long long mx = 0;
     bool badid = false;
-    auto flush = [&]() {
-        if (cur >= 0) {
-            unsigned* slot = tab_s + cur * C;
-            touched[cur] = 1;
-#pragma unroll
-            for (int ci = 0; ci < C; ++ci) {
-                const unsigned e = f32_to_ordered(acc[ci]);
-                if (e > slot[ci]) atomicMax(slot + ci, e);
-            }
-        }
-    };
+    // Every pixel probes its region's private row (the warp executes the same instructions whatever the ids are, so a
+    // per-thread run-length compression only adds divergence); the atomic is issued only when a slot would be raised,
+    // which happens O(log n) times per slot.
     for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
         const int64_t n0 = g * VEC;
         int64_t id[VEC];
@@ -306,18 +296,21 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
             if (r64 < 0 || r64 >= R) { badid = true; continue; }
             mx = max(mx, r64);
             const int r = (int)r64;
-            if (r != cur) {
-                flush();
-                cur = r;
+            if (i == 0 || r64 != id[i > 0 ? i - 1 : 0]) touched[r] = 1;
+            unsigned* slot = tab_s + r * CP;
+            unsigned old[CP];
 #pragma unroll
-                for (int ci = 0; ci < C; ++ci) acc[ci] = v[ci][i];
-            } else {
+            for (int q = 0; q < CP / 4; ++q) {
+                const uint4 o4 = *reinterpret_cast<const uint4*>(slot + 4 * q);
+                old[4 * q] = o4.x; old[4 * q + 1] = o4.y; old[4 * q + 2] = o4.z; old[4 * q + 3] = o4.w;
+            }
 #pragma unroll
-                for (int ci = 0; ci < C; ++ci) acc[ci] = fmaxf(acc[ci], v[ci][i]);
+            for (int ci = 0; ci < C; ++ci) {
+                const unsigned e = f32_to_ordered(v[ci][i]);
+                if (e > old[ci]) atomicMax(slot + ci, e);
             }
         }
     }
-    flush();
     if (badid && status) atomicOr(status, 2);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -335,7 +328,7 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
         for (int ci = 0; ci < C; ++ci) old[ci] = ld_cg_u32(tab + r * C + ci);
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) {
-            const unsigned e = tab_s[r * C + ci];
+            const unsigned e = tab_s[r * CP + ci];
             if (e > old[ci]) atomicMax(tab + r * C + ci, e);
         }
     }
@@ -556,7 +549,7 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
                        unsigned* table, int64_t* maxid_out, int* status, float* tail_sw, int* tail_done, float temp,
                        unsigned* zero_words, int n_zero, cudaStream_t st) {
     const bool vec = (N % 4 == 0) && (sb % 4 == 0) && (sc % 4 == 0) && uem_aligned16(src) && uem_aligned16(index);
-    const size_t smem = ((size_t)R * c * 4 + (size_t)((R + 3) / 4) * 4 + 15) & ~(size_t)15;
+    const size_t smem = ((size_t)R * ((c + 3) & ~3) * 4 + (size_t)((R + 3) / 4) * 4 + 15) & ~(size_t)15;
     UEM_REQUIRE(smem <= 200 * 1024, "uem_region_max_f32: region table (%lld x %d) exceeds shared memory", (long long)R, c);
     // the kernel is compiled for <= 64 registers (1024 threads per SM): two CTAs of 512 threads per SM when two private
     // tables fit, otherwise a single 1024-thread CTA; one wave
@@ -594,7 +587,7 @@ int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, c
                          unsigned* cnt, int* status, cudaStream_t st) {
     const int kop = (op == UEM_REDUCE_MAX) ? UEM_REDUCE_MAX : UEM_REDUCE_SUM;
     const bool vec = (sn == 1) && (N % 4 == 0) && (sb % 4 == 0) && (sc % 4 == 0) && uem_aligned16(src) && uem_aligned16(index);
-    if (kop == UEM_REDUCE_MAX && !cnt && sn == 1 && R * (c * 4 + 1) + 64 <= 200 * 1024)
+    if (kop == UEM_REDUCE_MAX && !cnt && sn == 1 && R * (((c + 3) & ~3) * 4 + 1) + 64 <= 200 * 1024)
         return uem_region_max_f32(src, sb, sc, index, b, N, c, R, table, nullptr, status, nullptr, nullptr, 1.0f, nullptr, 0, st);
     UEM_DISPATCH_C(c, {
         if (vec) {
