@@ -231,7 +231,11 @@ def main():
     miner = mining.ShardedMiner(al) if world > 1 else None
     ws = None
 
-    side = torch.cuda.Stream(device=dev)
+    # the target chain is the critical path: it runs on a high-priority stream, the source chain (prototype sums) on a
+    # low-priority one so that its CTAs fill the gaps instead of competing for the first wave
+    main_stream = torch.cuda.Stream(device=dev, priority=-1)
+    side = torch.cuda.Stream(device=dev, priority=0)
+    torch.cuda.set_stream(main_stream)
     proto_state = al.prototypes.clone()   # the replicated prototype bank: read by the refine chain, EMA-updated in place
     al.prototypes = proto_state
     n_pack = wl.c * wl.k + wl.c + 1
@@ -309,15 +313,15 @@ def main():
             for j, s in enumerate(sets):
                 if miner:
                     ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(ga):
+                    with torch.cuda.graph(ga, stream=main_stream):
                         phase_a(s, j)
                     miner.exchange(packed_bufs[j], out=gathered_bufs[j])
-                    with torch.cuda.graph(gb):
+                    with torch.cuda.graph(gb, stream=main_stream):
                         keep.append(phase_b(s, j))
                     graphs.append((ga, gb))
                 else:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=main_stream):
                         keep.append(step_resident(s))
                     graphs.append(g)
             barrier()

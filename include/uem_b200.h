@@ -171,7 +171,8 @@ UEM_API int uem_label_refine_f32(int views, const float* simi, const float* pred
  * soft (b,c,H,W) -> refined (b,c,H,W), hard (b,H,W) int64 (NULL = skip the selection); with hard, optionally the
  * entropy (b,H,W) and UVEM weight (b,H,W) of the refined map (balance.py:372,396-423; uvem_host as above).
  * ws: uem_mine_ws_bytes(...) bytes, ZERO-INITIALISED by the caller before its first use (every call leaves it clean
- * for the next one, so a persistent workspace needs no per-call memset; after a failed call zero it again);
+ * for the next one, so a persistent workspace needs no per-call memset; after a failed call zero it again; a
+ * workspace may be shared by calls with different views / feature shapes as long as b, c and R stay the same);
  * ws[0..3] int32 status word: bit 2 = superpixel id outside [0,R);
  * the class statistics table of `refined` is left at byte offset uem_mine_ws_stats_offset(...) of ws. */
 UEM_API int64_t uem_mine_ws_bytes(int b, int c, int H, int W, int h, int w, int k, int64_t R);

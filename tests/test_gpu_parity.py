@@ -365,3 +365,77 @@ def test_no_cpu_fallback(dev):
     from uemda_b200 import _lib, ops
     with pytest.raises(_lib.UemLibraryError):
         ops.class_max(torch.rand(1, 3, 8, 8))  # CPU tensor: must raise, never fall back
+
+
+# ------------------------------------------------------------------------------------ workspace / chain housekeeping
+def _small_inputs(dev, seed=11):
+    from uemda_b200.synth import Workload, make_inputs
+    wl = Workload("ws", 2, 6, 64, 96, 64, 16, 24)
+    inp = make_inputs(wl, seed=seed)
+    return wl, inp, _to(inp, dev)
+
+
+def test_workspace_reuse_and_mixed_views(dev):
+    """The fused chain keeps its workspace self-cleaning: a persistent workspace reused across calls, view subsets and
+    the memset fallback path must give exactly what a fresh zeroed workspace gives."""
+    from uemda_b200 import _lib, mining
+    wl, inp, d = _small_inputs(dev)
+    R = int(inp["ignore_id"]) + 1
+    lib = _lib.load()
+    ws = torch.zeros(lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, R), dtype=torch.uint8, device=dev)
+
+    def run(views, ws_, **kw):
+        return mining.refine_select(views, d["soft"], 2.0, feat=d["feat"], prototypes=d["prototypes"], pred1=d["pred1"],
+                                    pred2=d["pred2"], sup=d["sup"], num_regions=R, select=(0.8, 0.6, -1), ws=ws_, **kw)
+
+    fresh = {v: run(v, None) for v in (7, 4, 3, 6)}
+    for v in (7, 7, 4, 3, 7, 6, 7):
+        got = run(v, ws)
+        _eq(got[0], fresh[v][0], "refined, views=%d on a reused workspace" % v)
+        _eq(got[1], fresh[v][1], "hard, views=%d on a reused workspace" % v)
+    # entropy / UVEM weight variant leaves the workspace just as clean
+    a = run(7, ws, uvem=(0.2, 0.7, 4.0))
+    b2 = run(7, ws, uvem=(0.2, 0.7, 4.0))
+    for x, y in zip(a, b2):
+        _eq(x, y, "repeat with uvem outputs")
+
+
+def test_external_ignored_id_matches_internal(dev):
+    """Multi-GPU form: the batch-global max id supplied by the caller (after an all-reduce) == computed in the chain."""
+    from uemda_b200 import mining, ops
+    wl, inp, d = _small_inputs(dev, seed=12)
+    R = int(inp["ignore_id"]) + 1
+    kw = dict(feat=d["feat"], prototypes=d["prototypes"], pred1=d["pred1"], pred2=d["pred2"], sup=d["sup"], num_regions=R,
+              select=(0.8, 0.6, -1))
+    ref = mining.refine_select(7, d["soft"], 2.0, **kw)
+    ign = ops.i64_minmax(d["sup"])[1:].clone()
+    got = mining.refine_select(7, d["soft"], 2.0, ignored_id=ign, **kw)
+    _eq(got[0], ref[0], "refined with external ignored id")
+    _eq(got[1], ref[1], "hard with external ignored id")
+    # a different ignored id really changes which pixels the superpixel view skips
+    other = torch.zeros_like(ign)
+    diff = mining.refine_select(7, d["soft"], 2.0, ignored_id=other, **kw)
+    assert not torch.equal(diff[0], ref[0])
+
+
+def test_three_phase_miner_equals_update_prototype(dev):
+    """ShardedMiner.local_stats -> exchange -> apply at world size 1 == Aligner.update_prototype."""
+    from uemda_b200 import mining
+    from uemda_b200.gast.alignment import Aligner, DownscaleLabel
+    wl, inp, d = _small_inputs(dev, seed=13)
+
+    def fresh():
+        al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c, decay=0.996)
+        al.downscale_gt = DownscaleLabel(wl.scale, wl.c, -1, 0.75)
+        al.prototypes = d["prototypes"].clone()
+        return al
+
+    a = fresh()
+    down_a = a.update_prototype(d["feat_s"], d["label_s"])
+    b2 = fresh()
+    miner = mining.ShardedMiner(b2)
+    packed, down_b = miner.local_stats(d["sup"], d["feat_s"], d["label_s"])
+    ignored = miner.apply(miner.exchange(packed), in_place=True)
+    _eq(down_b, down_a, "down-scaled labels")
+    _eq(b2.prototypes, a.prototypes, "prototypes after the three-phase update")
+    assert int(ignored) == int(d["sup"].max())

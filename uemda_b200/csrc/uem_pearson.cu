@@ -10,6 +10,7 @@
 // the residual mean(g)*sum(pc_j) is subtracted anyway).  HBM-bound on feat: 4k B per feature pixel.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -39,8 +40,13 @@ __global__ void __launch_bounds__(256) proto_center_kernel(const float* __restri
     float s2 = 0.f, s1 = 0.f;
     for (int i = threadIdx.x; i < k; i += 256) {
         float d = p[i] - mean;
-        if (transposed) pc[(int64_t)i * kPcStride + j] = d;
-        else pc[(int64_t)j * k + i] = d;
+        if (transposed) {
+            pc[(int64_t)i * kPcStride + j] = d;
+            if (j == 0)  // unused class slots of the (k,8) table stay 0
+                for (int u = gridDim.x; u < kPcStride; ++u) pc[(int64_t)i * kPcStride + u] = 0.f;
+        } else {
+            pc[(int64_t)j * k + i] = d;
+        }
         s2 += d * d;
         s1 += d;
     }
@@ -368,7 +374,6 @@ extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_
     float* pc = (float*)ws;
     float* stats = pc + (int64_t)kPcStride * k;
     const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
-    UEM_CUDA(cudaMemsetAsync(pc, 0, (size_t)kPcStride * k * sizeof(float), st));  // unused class slots stay 0
     const bool tma = vec && hw < (1 << 30) && k >= kKT;
     UEM_DISPATCH_C(m, {
         proto_center_kernel<<<C, 256, 0, st>>>(protos, k, 1, pc, stats);
@@ -381,6 +386,7 @@ extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_
             // split k over a cluster so that ~2 CTAs per SM are busy, each with at least 4 tiles of its own
             int KS = 1;
             while (KS < 8 && (int64_t)ptiles * b * KS * 2 <= 2 * UEM_SMS && k / (KS * 2) >= 4 * kKT) KS *= 2;
+            if (getenv("UEM_PEARSON_KS")) KS = atoi(getenv("UEM_PEARSON_KS"));  // development knob
             const int kper = ((k + KS - 1) / KS + kKT - 1) / kKT * kKT;
             const size_t smem = (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4 + 2 * kStages * 8 + (size_t)kPT * (2 + C) * 4;
             UEM_CUDA(cudaFuncSetAttribute(pearson_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -954,28 +954,33 @@ extern "C" int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, cons
 // refined map), one C call, no host sync.  tools/train_ssl_uem.py:209-214, balance.py:372-396.
 // ws layout (all 16-byte aligned):
 //   [0]      status   int32[4]   bit1: label out of range, bit2: superpixel id outside [0,R)
-//   [16]     simi     f32[b*c*h*w]
-//            pearson ws (uem_pearson_ws_bytes)
-//            sw       f32[b*R*CP]  per-region superpixel-view weights
-//            --- zeroed by ONE memset per call ---
+//   [16]     --- self-cleaned block: zero on entry, zero again on exit; position depends on (b, c, R) only ---
 //            maxid    int64[2]     [0] = batch max superpixel id (alignment.py:241), ids are >= 0
+//            done     i32[b]       per-image arrival counters of the region-max kernel
 //            stats    u32[b*(c+2)] class stats of the refined map (ordered-encoded, atomically raised)
 //            region   u32[b*R*c]   ordered-encoded region maxima
+//            --- plain scratch ---
+//            simi     f32[b*c*h*w]
+//            pearson ws (uem_pearson_ws_bytes)
+//            sw       f32[b*(R+1)*CP] per-region superpixel-view weights (+ column tables)
 // ------------------------------------------------------------------------------------------------
 struct MineLayout {
-    int64_t simi, pearson, sw, zero_begin, maxid, done, stats, region, end;
+    int64_t simi, pearson, sw, zero_begin, zero_end, maxid, done, stats, region, end;
 };
 static MineLayout mine_layout(int b, int c, int W, int h, int w, int k, int64_t R) {
+    // The self-cleaned block comes first and depends on (b, c, R) only, so calls with different view subsets /
+    // feature shapes on the same workspace agree on where it lives.
     MineLayout L;
     int64_t n = 16;
-    L.simi = n; n += align16((int64_t)b * c * h * w * 4);
-    L.pearson = n; n += align16(uem_pearson_ws_bytes(c, k));
-    L.sw = n; n += uem_label_refine_ws_bytes(b, c, R, W);
     L.zero_begin = n;
     L.maxid = n; n += 16;
     L.done = n; n += align16((int64_t)b * 4);
     L.stats = n; n += uem_class_stats_bytes(b, c);
     L.region = n; n += align16((int64_t)b * R * c * 4);
+    L.zero_end = n;
+    L.simi = n; n += align16((int64_t)b * c * h * w * 4);
+    L.pearson = n; n += align16(uem_pearson_ws_bytes(c, k));
+    L.sw = n; n += uem_label_refine_ws_bytes(b, c, R, W);
     L.end = n;
     return L;
 }
@@ -1005,7 +1010,9 @@ int side_stream(SideStream** out) {
     UEM_REQUIRE(dev >= 0 && dev < 16, "uem_mine_refine_select_f32: device index %d out of range", dev);
     SideStream& s = side[dev];
     if (s.device != dev) {
-        UEM_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        int least = 0, greatest = 0;
+        UEM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        UEM_CUDA(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, greatest));  // part of the critical chain
         UEM_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         UEM_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
         s.device = dev;
@@ -1039,7 +1046,7 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     // zeroes the table rows and arrival counters again, the selection kernel zeroes the max-id slot -- so no memset
     // node sits on the critical path.  Every other configuration zeroes the region before and after the call.
     const bool selfclean = (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)cp_of(c) * 4 + 1) + 64 <= 200 * 1024;
-    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.end - L.zero_begin), st));
+    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));
     // fork: the feature pass runs on the side stream while the region-max pass (below) runs on the caller's stream
     SideStream* side = nullptr;
     const bool fork = (views & UEM_VIEW_PROTO) && (views & UEM_VIEW_SUP);
@@ -1091,6 +1098,6 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
             return rc;
     }
     if (selfclean && own_maxid && !select) UEM_CUDA(cudaMemsetAsync(maxid, 0, 16, st));
-    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.stats - L.zero_begin), st));  // leave maxid/done clean
+    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));  // leave the block clean
     return 0;
 }

@@ -47,7 +47,7 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
         if h:
             assert pred1.shape[-2:] == (h, w), "feature map and logits must share their resolution"
         h, w = pred1.shape[-2:]
-    R = 0
+    R = int(num_regions) if num_regions is not None else 0  # the workspace layout depends on (b, c, R): keep R per workspace
     if views & ops.VIEW_SUP:
         sup = L.i64c(sup.detach())
         assert sup.numel() == b * H * W
@@ -81,9 +81,10 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
         L.ptr(hard), uv, L.ptr(ent), L.ptr(wgt), L.ptr(ws), L.stream_of(soft)))
     # [class maxima | -min | bad] of `refined`, reused by pseudo_selection() so it needs no second max pass
-    off = lib.uem_mine_ws_stats_offset(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
-    stats = ws[off:off + b * (c + 2) * 4].view(torch.int32).view(b, c + 2).clone()
-    refined._uem_stats = (stats, refined._version)
+    if select is None:  # the drop-in pairing label_refine -> pseudo_selection: hand the class statistics over
+        off = lib.uem_mine_ws_stats_offset(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
+        stats = ws[off:off + b * (c + 2) * 4].view(torch.int32).view(b, c + 2).clone()
+        refined._uem_stats = (stats, refined._version)
     if want_entropy or uvem is not None:
         return refined, hard, ent, wgt
     return refined, hard
