@@ -218,6 +218,11 @@ UEM_API int uem_class_weight_lookup_f32(const int64_t* label, int64_t n, int c, 
                                 const float* table, float* out, void* stream);
 UEM_API int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float hi, int64_t* hist, void* stream);
 
+/* ---- offline pseudo-label regeneration (next row) ------------------------------
+ * pseudo_generation.py:150-151, vis_corrected_pseudo_labels.py:191: the map written to disk is
+ * uint8(label + 1), i.e. ignore (-1) -> 0, class j -> j+1 (numpy astype semantics: modulo 256). */
+UEM_API int uem_label_plus1_u8_i64(const int64_t* label, int64_t n, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -439,3 +439,43 @@ def test_three_phase_miner_equals_update_prototype(dev):
     _eq(down_b, down_a, "down-scaled labels")
     _eq(b2.prototypes, a.prototypes, "prototypes after the three-phase update")
     assert int(ignored) == int(d["sup"].max())
+
+
+def test_regeneration_driver_matches_oracle_per_tile(dev):
+    """Next row: offline regeneration = refine -> select -> uint8(label+1), reference batch size 1."""
+    from oracle import uem_oracle as O
+    from uemda_b200.regen import PseudoLabelRegenerator
+    from uemda_b200.gast.alignment import Aligner
+    from uemda_b200.synth import Workload, make_inputs
+    wl = Workload("regen", 3, 6, 64, 64, 32, 16, 16)
+    inp = make_inputs(wl, seed=21)
+    # make tile 2 disagree on the max id so that the per-tile fallback is exercised too
+    sup = inp["sup"].clone()
+    sup[2][sup[2] == sup[2].max()] = int(sup[2].max()) + 3
+    al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c)
+    al.prototypes = inp["prototypes"].to(dev)
+    want = []
+    for i in range(wl.b):  # the reference walks the set with batch_size=1
+        r = O.label_refine(sup[i:i + 1], inp["feat"][i:i + 1], [inp["pred1"][i:i + 1], inp["pred2"][i:i + 1]], inp["soft"][i:i + 1],
+                           inp["prototypes"], mode="all", temp=2.0)
+        want.append(O.pseudo_select(r, 0.8, 0.6, -1))
+    want = (torch.cat(want) + 1).to(torch.uint8)
+    batches = [{"soft": inp["soft"][:2].pin_memory(), "sup": sup[:2].pin_memory(), "feat": inp["feat"][:2].pin_memory(),
+                "preds": [inp["pred1"][:2].pin_memory(), inp["pred2"][:2].pin_memory()], "names": ["t0", "t1"]},
+               {"soft": inp["soft"][2:].pin_memory(), "sup": sup[2:].pin_memory(), "feat": inp["feat"][2:].pin_memory(),
+                "preds": [inp["pred1"][2:].pin_memory(), inp["pred2"][2:].pin_memory()], "names": ["t2"]}]
+    got = {}
+    regen = PseudoLabelRegenerator(al, 0.8, 0.6, mode="all", temp=2.0, num_regions=int(sup.max()) + 1)
+    n = regen.run(batches, lambda names, arr: got.update({nm: arr[j].copy() for j, nm in enumerate(names)}))
+    assert n == 3 and sorted(got) == ["t0", "t1", "t2"]
+    out = torch.from_numpy(np.stack([got["t0"], got["t1"], got["t2"]]))
+    assert out.dtype == torch.uint8
+    mism = int((out != want).sum())
+    assert mism <= 2, "regenerated label mismatches vs oracle: %d" % mism
+    # mixed batch (tiles 1 and 2 disagree on the ignored id) goes through the tile-by-tile path and agrees with the above
+    mixed = regen.process(inp["soft"][1:].to(dev), sup[1:].to(dev), inp["feat"][1:].to(dev),
+                          [inp["pred1"][1:].to(dev), inp["pred2"][1:].to(dev)])
+    _eq(mixed, out[1:], "mixed-batch regeneration")
+    # selection-only variant (pseudo_generation.py:138-151) is bit-exact
+    plain = PseudoLabelRegenerator(None, 0.8, 0.6, refine=False).process(inp["soft"].to(dev))
+    _eq(plain, (O.pseudo_select(inp["soft"], 0.8, 0.6, -1) + 1).to(torch.uint8), "selection-only regeneration")

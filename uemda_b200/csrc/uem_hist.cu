@@ -91,6 +91,26 @@ __global__ void __launch_bounds__(kThreads) hist_f32_kernel(const float* __restr
         if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
 }
 
+// offline regeneration: the label map written to disk is uint8(label + 1), ignore (-1) -> 0
+// (pseudo_generation.py:150-151, vis_corrected_pseudo_labels.py:191)
+__global__ void __launch_bounds__(kThreads) label_plus1_u8_kernel(const int64_t* __restrict__ label, int64_t n, int vec,
+                                                                  uint8_t* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nth = (int64_t)gridDim.x * kThreads;
+    if (vec) {  // 4 labels (2 x 128-bit) -> one 32-bit store
+        for (int64_t i = tid; i < n / 4; i += nth) {
+            int64_t a, b2, c2, d;
+            ldg_i64x2(label + 4 * i, a, b2);
+            ldg_i64x2(label + 4 * i + 2, c2, d);
+            const unsigned w = (unsigned)(uint8_t)(a + 1) | ((unsigned)(uint8_t)(b2 + 1) << 8) | ((unsigned)(uint8_t)(c2 + 1) << 16) |
+                               ((unsigned)(uint8_t)(d + 1) << 24);
+            reinterpret_cast<unsigned*>(out)[i] = w;
+        }
+        for (int64_t i = (n / 4) * 4 + tid; i < n; i += nth) out[i] = (uint8_t)(label[i] + 1);
+    } else {
+        for (int64_t i = tid; i < n; i += nth) out[i] = (uint8_t)(label[i] + 1);
+    }
+}
+
 }  // namespace
 
 extern "C" int uem_class_hist_i64(const int64_t* label, int64_t n, int c, int64_t ignore_label, int64_t* hist, void* stream) {
@@ -120,6 +140,15 @@ extern "C" int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float
     if (n == 0) return 0;
     const int grid = (int)min((int64_t)UEM_SMS * 4, (n + kThreads - 1) / kThreads);
     hist_f32_kernel<<<grid, kThreads, bins * sizeof(unsigned), (cudaStream_t)stream>>>(x, n, bins, lo, hi, (unsigned long long*)hist);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_label_plus1_u8_i64(const int64_t* label, int64_t n, uint8_t* out, void* stream) {
+    UEM_REQUIRE(label && out && n > 0, "uem_label_plus1_u8_i64: bad arguments");
+    const int vec = uem_aligned16(label) && ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
+    const int grid = (int)min((int64_t)UEM_SMS * 8, (n / 4 + kThreads - 1) / kThreads + 1);
+    label_plus1_u8_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(label, n, vec, out);
     UEM_CHECK_LAUNCH();
     return 0;
 }

@@ -381,3 +381,14 @@ def hist_f32(x, bins, lo, hi):
     hist = torch.zeros(bins, dtype=torch.int64, device=x.device)
     L.check(lib.uem_hist_f32(L.ptr(x), x.numel(), int(bins), f32(lo), f32(hi), L.ptr(hist), L.stream_of(x)))
     return hist
+
+
+# --------------------------------------------------------------------------------------------- regeneration
+def label_plus1_u8(label):
+    """uint8(label + 1): the on-disk form of a hard pseudo-label map (pseudo_generation.py:150-151)."""
+    L.require_cuda(label)
+    label = L.i64c(label.detach())
+    lib = L.bind(label)
+    out = torch.empty(label.shape, dtype=torch.uint8, device=label.device)
+    L.check(lib.uem_label_plus1_u8_i64(L.ptr(label), label.numel(), L.ptr(out), L.stream_of(label)))
+    return out
