@@ -246,14 +246,13 @@ def main():
     ev_a = [torch.cuda.Event() for _ in range(args.sets)]
     ev_b = [torch.cuda.Event() for _ in range(args.sets)]
 
-    def source_stats(s):
+    def source_stats(s, fold=True):
         """source-side chain on the second stream: DownscaleLabel -> masked prototype sums (independent of the target chain)"""
         cur = torch.cuda.current_stream(dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             down = al.downscale_gt(s["label_s"])
-            sums, counts = ops.proto_accumulate(s["feat_s"], down, wl.c, -1)
-        return sums, counts
+            return ops.proto_accumulate(s["feat_s"], down, wl.c, -1, fold=fold)
 
     def target_chain(s, ignored):
         return mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=proto_state, pred1=s["pred1"],
@@ -265,10 +264,10 @@ def main():
         streams; the EMA writes the prototype bank in place once the target chain (its last reader) is enqueued."""
         nonlocal ws
         cur = torch.cuda.current_stream(dev)
-        sums, counts = source_stats(s)
+        partials = source_stats(s, fold=False)
         out = target_chain(s, None)
         cur.wait_stream(side)
-        ops.proto_finalize(sums, counts, proto_state, eps=al.eps, decay=DECAY, want_local=False, out=proto_state)
+        ops.proto_fold_finalize(partials, proto_state, eps=al.eps, decay=DECAY, out=proto_state)
         return out
 
     # multi-GPU: the batch is sharded by image; the only exchange is ONE all_gather of [prototype sums | counts | max id]

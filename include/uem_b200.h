@@ -200,6 +200,10 @@ UEM_API int uem_proto_weight_4pixel_f32(const float* simi, int h, int w, const i
 UEM_API int64_t uem_proto_accum_ws_bytes(int b, int c, int k);
 UEM_API int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t hw, const int64_t* label, int c,
                              int64_t ignore_label, float* sums, int64_t* counts, void* ws, void* stream);
+/* sums == counts == NULL: leave the per-image partial sums in ws for uem_proto_fold_finalize_ema_f32, which folds them
+ * (image order), applies the keep-old rule and the EMA in one launch (proto_new may alias proto_old). */
+UEM_API int uem_proto_fold_finalize_ema_f32(const void* ws, int b, int c, int k, const float* proto_old, float eps,
+                                    float one_minus_decay, float decay, float* proto_new, void* stream);
 UEM_API int64_t uem_proto_accum_soft_ws_bytes(int b, int c, int k, int h, int w);
 UEM_API int uem_proto_accum_soft_f32(const float* feat, int b, int k, int h, int w, const float* soft, int c,
                              int H, int W, float* sums, void* ws, void* stream);

@@ -479,3 +479,17 @@ def test_regeneration_driver_matches_oracle_per_tile(dev):
     # selection-only variant (pseudo_generation.py:138-151) is bit-exact
     plain = PseudoLabelRegenerator(None, 0.8, 0.6, refine=False).process(inp["soft"].to(dev))
     _eq(plain, (O.pseudo_select(inp["soft"], 0.8, 0.6, -1) + 1).to(torch.uint8), "selection-only regeneration")
+
+
+def test_fused_fold_finalize_equals_two_step(dev):
+    from uemda_b200 import ops
+    wl, inp, d = _small_inputs(dev, seed=14)
+    down = ops.downscale_label(d["label_s"], wl.scale, wl.c)
+    sums, counts = ops.proto_accumulate(d["feat_s"], down, wl.c)
+    _, want = ops.proto_finalize(sums, counts, d["prototypes"], decay=0.996, want_local=False)
+    part = ops.proto_accumulate(d["feat_s"], down, wl.c, fold=False)
+    got = ops.proto_fold_finalize(part, d["prototypes"], decay=0.996)
+    _eq(got, want, "fused fold + finalize")
+    state = d["prototypes"].clone()
+    ops.proto_fold_finalize(part, state, decay=0.996, out=state)
+    _eq(state, want, "in-place fused fold + finalize")

@@ -57,6 +57,7 @@ SIGNATURES = {
     "uem_proto_accum_soft_ws_bytes": (_L, [_I, _I, _I, _I, _I]),
     "uem_proto_accum_nchw_f32": (_I, [_P, _I, _I, _L, _P, _I, _L, _P, _P, _P, _P]),
     "uem_proto_accum_soft_f32": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "uem_proto_fold_finalize_ema_f32": (_I, [_P, _I, _I, _I, _P, _F, _F, _F, _P, _P]),
     "uem_proto_finalize_ema_f32": (_I, [_P, _P, _L, _P, _I, _I, _F, _F, _F, _P, _P, _P]),
     "uem_class_hist_i64": (_I, [_P, _L, _I, _L, _P, _P]),
     "uem_class_weight_lookup_f32": (_I, [_P, _L, _I, _L, _P, _P, _P]),

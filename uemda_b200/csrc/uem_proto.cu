@@ -539,6 +539,26 @@ __global__ void __launch_bounds__(256) proto_finalize_kernel(const float* __rest
         proto_new[i] = __fadd_rn(__fmul_rn(one_minus_decay, local), __fmul_rn(decay, proto_old[i]));
 }
 
+// fold of the per-image partials (image order, deterministic) + local mean + keep-old rule + EMA in ONE launch
+// (alignment.py:347-353, :463-466): the single-GPU step needs neither the folded sums nor a separate fold kernel
+__global__ void __launch_bounds__(256) proto_fold_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial,
+                                                                  int b, int c, int k, const float* __restrict__ proto_old, float eps,
+                                                                  float one_minus_decay, float decay, float* __restrict__ proto_new) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= c * k) return;
+    const int ci = i / k;
+    float s = 0.f;
+    int64_t n = 0;
+    for (int bi = 0; bi < b; ++bi) {
+        s += partial[(int64_t)bi * c * k + i];
+        n += cnt_partial[bi * c + ci];
+    }
+    const float old = proto_old[i];
+    float local = s / ((float)n + eps);
+    if (n < 1) local = old;
+    proto_new[i] = __fadd_rn(__fmul_rn(one_minus_decay, local), __fmul_rn(decay, old));
+}
+
 }  // namespace
 
 extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W, int scale, int n_classes, int64_t ignore_label,
@@ -586,7 +606,7 @@ extern "C" int64_t uem_proto_accum_soft_ws_bytes(int b, int c, int k, int h, int
 
 extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t hw, const int64_t* label, int c,
                                         int64_t ignore_label, float* sums, int64_t* counts, void* ws, void* stream) {
-    UEM_REQUIRE(feat && label && sums && counts && ws && b > 0 && k > 0 && hw > 0, "uem_proto_accum_nchw_f32: bad arguments");
+    UEM_REQUIRE(feat && label && ws && b > 0 && k > 0 && hw > 0 && (!sums == !counts), "uem_proto_accum_nchw_f32: bad arguments");
     UEM_REQUIRE(hw <= 200 * 1024, "uem_proto_accum_nchw_f32: %lld feature pixels per image exceed the shared-memory label stage", (long long)hw);
     cudaStream_t st = (cudaStream_t)stream;
     float* partial = (float*)ws;
@@ -619,8 +639,19 @@ extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t
             proto_accum_kernel<C, 1><<<grid, kAccThreads, smem, st>>>(feat, k, hw, label, ignore_label, partial, cnt_partial);
         }
     });
-    proto_fold_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, st>>>(partial, cnt_partial, b, c * k, c, sums, counts);
-    UEM_CHECK_LAUNCH_N(2);
+    if (sums) proto_fold_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, st>>>(partial, cnt_partial, b, c * k, c, sums, counts);
+    UEM_CHECK_LAUNCH_N(sums ? 2 : 1);
+    return 0;
+}
+
+extern "C" int uem_proto_fold_finalize_ema_f32(const void* ws, int b, int c, int k, const float* proto_old, float eps,
+                                               float one_minus_decay, float decay, float* proto_new, void* stream) {
+    UEM_REQUIRE(ws && proto_old && proto_new && b > 0 && c > 0 && k > 0, "uem_proto_fold_finalize_ema_f32: bad arguments");
+    const float* partial = (const float*)ws;
+    const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
+    proto_fold_finalize_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, proto_old, eps,
+                                                                                                one_minus_decay, decay, proto_new);
+    UEM_CHECK_LAUNCH();
     return 0;
 }
 

@@ -306,20 +306,36 @@ def proto_weight_4pixel(simi, hard, ignore_label=-1, eps=1e-7):
 
 
 # --------------------------------------------------------------------------------------------- a10-a12
-def proto_accumulate(feat, label_down, class_num, ignore_label=-1):
-    """Masked per-class feature sums (c,k) fp32 and counts (c,) int64 (alignment.py:341-348)."""
+def proto_accumulate(feat, label_down, class_num, ignore_label=-1, fold=True):
+    """Masked per-class feature sums (c,k) fp32 and counts (c,) int64 (alignment.py:341-348).
+    fold=False: returns the opaque per-image partials (for proto_fold_finalize) instead."""
     L.require_cuda(feat, label_down)
     feat = L.f32c(feat.detach())
     label = L.i64c(label_down.detach())
     b, k, h, w = feat.shape
     assert label.numel() == b * h * w, "label must be at feature resolution"
     lib = L.bind(feat)
-    sums = torch.empty((class_num, k), dtype=torch.float32, device=feat.device)
-    counts = torch.empty((class_num,), dtype=torch.int64, device=feat.device)
+    sums = torch.empty((class_num, k), dtype=torch.float32, device=feat.device) if fold else None
+    counts = torch.empty((class_num,), dtype=torch.int64, device=feat.device) if fold else None
     ws = L.workspace(lib.uem_proto_accum_ws_bytes(b, class_num, k), feat)
     L.check(lib.uem_proto_accum_nchw_f32(L.ptr(feat), b, k, h * w, L.ptr(label), class_num, int(ignore_label), L.ptr(sums),
                                          L.ptr(counts), L.ptr(ws), L.stream_of(feat)))
+    if not fold:
+        return ws, (b, class_num, k)
     return sums, counts
+
+
+def proto_fold_finalize(partials, proto_old, eps=1e-7, decay=0.999, out=None):
+    """partials from proto_accumulate(fold=False) -> EMA-updated prototypes in one launch (alignment.py:347-353,463-466).
+    out may be ``proto_old`` itself."""
+    ws, (b, c, k) = partials
+    L.require_cuda(ws, proto_old)
+    lib = L.bind(ws)
+    proto_old = L.f32c(proto_old.detach())
+    new = out if out is not None else torch.empty_like(proto_old)
+    L.check(lib.uem_proto_fold_finalize_ema_f32(L.ptr(ws), b, c, k, L.ptr(proto_old), f32(eps), f32(1.0 - decay), f32(decay),
+                                                L.ptr(new), L.stream_of(ws)))
+    return new
 
 
 def proto_accumulate_soft(feat, soft):
