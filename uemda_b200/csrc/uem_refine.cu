@@ -44,9 +44,6 @@ int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats
 #ifndef UEM_REFINE_EXP
 #define UEM_REFINE_EXP 0    // development experiments: 1 = no soft/id loads (compute floor), 2 = no view math (memory floor)
 #endif
-#ifndef UEM_XTAB_GLOBAL
-#define UEM_XTAB_GLOBAL 0   // 1: horizontal-weight table read from global (L1) instead of a per-CTA shared copy
-#endif
 
 #ifndef UEM_NO_PACKED
 #define UEM_NO_PACKED 0     // development experiment: 1 = scalar FFMA/FMUL/FADD instead of the packed fp32x2 forms
@@ -91,7 +88,6 @@ struct RefineParams {
     int div_temp;           // temp is not a power of two: the staged logits are divided (one rounding) instead
     const int64_t* sup;
     const float* sw;        // (b,R+1,CP) per-region superpixel-view weights
-    const float4* xtab;     // (W/4, 4) horizontal 3-tap weights per 4-pixel group (TMA kernel)
     int64_t R;
     const int64_t* ignored_id;
     const float* soft;
@@ -422,24 +418,41 @@ __device__ __forceinline__ void xtab_entry(float4* e, int g, int w, float sx) {
     e[2] = make_float4(wb[0], wb[1], wb[2], wb[3]);
     e[3] = make_float4(wc[0], wc[1], wc[2], wc[3]);
 }
+// compact form (32 bytes per group, used when the full table would cost a resident CTA): column offset, a 4-bit mask of
+// the pixels that sit in the second interval, and the four l1; l0 = 1 - l1 is recomputed exactly as make_lerp does
+template <int C>
+__device__ __forceinline__ void xtab_entry_compact(float4* e, int g, int w, float sx) {
+    const int x0 = g * 4;
+    const int a = make_lerp(x0, w, sx).i0;
+    float l1[4];
+    int mask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const Lerp lx = make_lerp(x0 + i, w, sx);
+        l1[i] = lx.l1;
+        mask |= (lx.i0 != a) << i;
+    }
+    e[0] = make_float4(__int_as_float(a * Lay<C>::STRIDE), __int_as_float(mask), l1[0], l1[1]);
+    e[1] = make_float4(l1[2], l1[3], 0.f, 0.f);
+}
 
 struct TmaLayout {
     uint32_t stage_bytes, off_row, off_xt, off_raw, off_bar, total;
 };
-__host__ __device__ inline TmaLayout tma_layout(int C, int W, int w, int nstage) {
+__host__ __device__ inline TmaLayout tma_layout(int C, int W, int w, int nstage, int xc) {
     const int CP = (C + 3) & ~3;
     TmaLayout L;
     L.stage_bytes = (uint32_t)W * (4u * C + 8u);
     uint32_t n = (uint32_t)nstage * L.stage_bytes;
     L.off_row = n; n += 2u * (uint32_t)(w + 2) * 3u * CP * 4u;
-    L.off_xt = n; n += UEM_XTAB_GLOBAL ? 0u : (uint32_t)(W / 4) * 64u;
+    L.off_xt = n; n += (uint32_t)(W / 4) * (xc ? 32u : 64u);
     L.off_raw = n; n += ((2u * 3u * C * (uint32_t)w * 4u) + 15u) & ~15u;
     L.off_bar = n; n += 8u * (((uint32_t)nstage + 2u) & ~1u);  // full[nstage] + the raw-row barrier
     L.total = n;
     return L;
 }
 
-template <int C, int NSTAGE, int NT>
+template <int C, int NSTAGE, int NT, int XC>
 __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_kernel(const RefineParams p) {
     constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE, PC = Lay<C>::PC, NW = NT / 32;
     constexpr float kL2E = 1.4426950408889634f;
@@ -447,13 +460,9 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
     unsigned char* const smem_raw = smem_tma;
     __shared__ float red[NW][C + 2];
     const int W = p.W, w = p.w, H = p.H, groups = W >> 2;
-    const TmaLayout L = tma_layout(C, W, w, NSTAGE);
+    const TmaLayout L = tma_layout(C, W, w, NSTAGE, XC);
     float* rowbuf = reinterpret_cast<float*>(smem_raw + L.off_row);   // [2][w+2][STRIDE]
-#if UEM_XTAB_GLOBAL
-    const float4* __restrict__ xtab = p.xtab;
-#else
-    float4* xtab = reinterpret_cast<float4*>(smem_raw + L.off_xt);    // [groups][4]: {a, -, -, -}, wa[4], wb[4], wc[4]
-#endif
+    float4* xtab = reinterpret_cast<float4*>(smem_raw + L.off_xt);    // [groups][4]: {a, -, -, -}, wa[4], wb[4], wc[4] (or compact)
     float* raw = reinterpret_cast<float*>(smem_raw + L.off_raw);      // [2][3C][w]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
     const int rowlen = (w + 2) * STRIDE;
@@ -545,9 +554,10 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
             rowbuf[col * STRIDE + m * CP + C + slot] = -1e30f;
         }
     }
-#if !UEM_XTAB_GLOBAL
-    for (int g = threadIdx.x; g < groups; g += NT) xtab_entry<C>(xtab + 4 * g, g, w, p.sx);
-#endif
+    for (int g = threadIdx.x; g < groups; g += NT) {
+        if constexpr (XC) xtab_entry_compact<C>(xtab + 2 * g, g, w, p.sx);
+        else xtab_entry<C>(xtab + 4 * g, g, w, p.sx);
+    }
     // programmatic dependent launch: everything above touched only this kernel's inputs and its own shared memory;
     // the similarity map, the region weights and the ignored id are produced by the preceding kernels
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -583,13 +593,29 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
         const uint32_t Ru = (uint32_t)p.R;
         float nanacc = 0.f;  // s*0 accumulates to NaN iff a row sum was inf/NaN
         for (int g = threadIdx.x; g < groups; g += NT) {
-#if UEM_XTAB_GLOBAL
-            const float4 q0 = __ldg(xtab + g * 4), qa = __ldg(xtab + g * 4 + 1), qb = __ldg(xtab + g * 4 + 2), qc = __ldg(xtab + g * 4 + 3);
-#else
-            const float4 q0 = xtab[g * 4], qa = xtab[g * 4 + 1], qb = xtab[g * 4 + 2], qc = xtab[g * 4 + 3];
-#endif
-            const float wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w}, wc[4] = {qc.x, qc.y, qc.z, qc.w};
-            const float* col = row + __float_as_int(q0.x);
+            float wa[4], wb[4], wc[4];
+            int col_off;
+            if constexpr (XC) {
+                const float4 e0 = xtab[g * 2], e1 = xtab[g * 2 + 1];
+                col_off = __float_as_int(e0.x);
+                const int mask = __float_as_int(e0.y);
+                const float l1[4] = {e0.z, e0.w, e1.x, e1.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float l0 = 1.0f - l1[i];
+                    const bool d = (mask >> i) & 1;
+                    wa[i] = d ? 0.f : l0;
+                    wb[i] = d ? l0 : l1[i];
+                    wc[i] = d ? l1[i] : 0.f;
+                }
+            } else {
+                const float4 q0 = xtab[g * 4], qa = xtab[g * 4 + 1], qb = xtab[g * 4 + 2], qc = xtab[g * 4 + 3];
+                col_off = __float_as_int(q0.x);
+                wa[0] = qa.x; wa[1] = qa.y; wa[2] = qa.z; wa[3] = qa.w;
+                wb[0] = qb.x; wb[1] = qb.y; wb[2] = qb.z; wb[3] = qb.w;
+                wc[0] = qc.x; wc[1] = qc.y; wc[2] = qc.z; wc[3] = qc.w;
+            }
+            const float* col = row + col_off;
             float2 wgt2[PC][4];
 #if UEM_REFINE_EXP == 2
 #pragma unroll
@@ -711,11 +737,8 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
 template <int C>
 __global__ void __launch_bounds__(256) region_weight_kernel(const void* __restrict__ table, int encoded, int b, int64_t R,
                                                             const int64_t* __restrict__ ignored_ptr, float temp, float inv_temp,
-                                                            int div_temp, float* __restrict__ sw, float4* __restrict__ xtab,
-                                                            int groups, int w, float sx) {
+                                                            int div_temp, float* __restrict__ sw) {
     constexpr int CP = Lay<C>::CP;
-    if (xtab)  // horizontal-weight table of the TMA refine kernel (depends on the column only)
-        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) xtab_entry<C>(xtab + 4 * g, g, w, sx);
     const int64_t rows = (int64_t)b * (R + 1);
     (void)ignored_ptr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
@@ -825,26 +848,31 @@ static int launch_refine_tma(RefineParams p, cudaStream_t st, bool pdl, bool* do
     *done = false;
     const int groups = p.W / 4;
     const int nt = groups > 128 ? 256 : 128;
-    const size_t s2 = tma_layout(C, p.W, p.w, 2).total, s3 = tma_layout(C, p.W, p.w, 3).total;
     const size_t budget = 200 * 1024;
-    if (s2 > budget) return 0;  // row too long for two stages: generic kernel
+    // resident CTAs per SM by shared memory (1 KB reserved per CTA) for {2,3} stages x {full, compact} column table
+    auto per_sm = [&](int nstage, int xc) -> size_t {
+        const size_t s = tma_layout(C, p.W, p.w, nstage, xc).total;
+        return s > budget ? 0 : (228 * 1024) / (s + 1024 + 256);
+    };
+    const size_t by_regs = (size_t)(UEM_REFINE_MINB * 128) / nt;  // what the register cap allows
+    if (per_sm(2, 1) == 0) return 0;  // row too long even for two stages: generic kernel
+    // the compact table only when the full one would cost a resident CTA; a third stage only when it is free
+    const int xc = (min(per_sm(2, 0), by_regs) < min(per_sm(2, 1), by_regs)) ? 1 : 0;
+    const bool three = per_sm(3, xc) >= min(per_sm(2, xc), by_regs) && per_sm(3, xc) > 0;
+    const size_t smem = tma_layout(C, p.W, p.w, three ? 3 : 2, xc).total;
     constexpr float kL2E = 1.4426950408889634f;
     p.map_scale[0] = kL2E;
     p.map_scale[1] = p.map_scale[2] = kL2E / p.temp;  // used when temp is a power of two (exact scaling)
-    const size_t per2 = (228 * 1024) / (s2 + 1024 + 256), per3 = (228 * 1024) / (s3 + 1024 + 256);
-#ifdef UEM_REFINE_FORCE3
-    const bool three = s3 <= budget;
-#else
-    const bool three = s3 <= budget && per3 >= per2;
-#endif
     int rc;
+#define UEM_LAUNCH_TMA(NS, NTH, XCV) rc = launch_persistent(refine_tma_kernel<C, NS, NTH, XCV>, p, NTH, smem, st, pdl)
     if (nt == 128) {
-        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 128>, p, 128, s3, st, pdl)
-                   : launch_persistent(refine_tma_kernel<C, 2, 128>, p, 128, s2, st, pdl);
+        if (three) { if (xc) UEM_LAUNCH_TMA(3, 128, 1); else UEM_LAUNCH_TMA(3, 128, 0); }
+        else { if (xc) UEM_LAUNCH_TMA(2, 128, 1); else UEM_LAUNCH_TMA(2, 128, 0); }
     } else {
-        rc = three ? launch_persistent(refine_tma_kernel<C, 3, 256>, p, 256, s3, st, pdl)
-                   : launch_persistent(refine_tma_kernel<C, 2, 256>, p, 256, s2, st, pdl);
+        if (three) { if (xc) UEM_LAUNCH_TMA(3, 256, 1); else UEM_LAUNCH_TMA(3, 256, 0); }
+        else { if (xc) UEM_LAUNCH_TMA(2, 256, 1); else UEM_LAUNCH_TMA(2, 256, 0); }
     }
+#undef UEM_LAUNCH_TMA
     *done = (rc == 0);
     return rc;
 }
@@ -888,16 +916,13 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     const bool vec = (W % 4 == 0) && uem_aligned16(soft) && uem_aligned16(out) && (!sup || uem_aligned16(sup));
     const bool fast = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2 && 3.0f * p.sx <= 0.999f &&
                       (w % 4 == 0) && uem_aligned16(simi) && uem_aligned16(pred1) && uem_aligned16(pred2);
-    float4* xt = sw_ws ? reinterpret_cast<float4*>(sw_ws + (int64_t)b * (R + 1) * cp_of(c)) : nullptr;  // 16-byte aligned (CP % 4 == 0)
-    p.xtab = xt;
     void *ev0 = nullptr, *ev1 = nullptr;
     int launched = 1, rc = 0;
     UEM_DISPATCH_C(c, {
         if ((views & UEM_VIEW_SUP) && !weights_ready) {
             const int64_t rows = (int64_t)b * (R + 1);
             region_weight_kernel<C><<<(int)min((int64_t)UEM_SMS * 4, (rows + 255) / 256), 256, 0, st>>>(
-                table, table_encoded, b, R, ignored_id, temp, 1.0f / temp, p.div_temp, sw_ws,
-                (UEM_XTAB_GLOBAL && fast) ? xt : nullptr, W / 4, w, p.sx);
+                table, table_encoded, b, R, ignored_id, temp, 1.0f / temp, p.div_temp, sw_ws);
             launched = 2;
         }
         uem_take_profile_events(&ev0, &ev1);
