@@ -188,13 +188,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
-#ifdef UEM_NO_MUFU
-    return fmaf(x, x, 1.0f);  // development experiment only: takes the XU pipe out of the picture
-#else
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
-#endif
 }
 // e_c = exp(z_c - max z) (one MUFU each; results below 2^-126 flush to 0, irrelevant for a softmax numerator),
 // returns S = sum e_c

@@ -10,7 +10,6 @@
 // the residual mean(g)*sum(pc_j) is subtracted anyway).  HBM-bound on feat: 4k B per feature pixel.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
-#include <stdlib.h>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -386,7 +385,6 @@ extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_
             // split k over a cluster so that ~2 CTAs per SM are busy, each with at least 4 tiles of its own
             int KS = 1;
             while (KS < 8 && (int64_t)ptiles * b * KS * 2 <= 2 * UEM_SMS && k / (KS * 2) >= 4 * kKT) KS *= 2;
-            if (getenv("UEM_PEARSON_KS")) KS = atoi(getenv("UEM_PEARSON_KS"));  // development knob
             const int kper = ((k + KS - 1) / KS + kKT - 1) / kKT * kKT;
             const size_t smem = (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4 + 2 * kStages * 8 + (size_t)kPT * (2 + C) * 4;
             UEM_CUDA(cudaFuncSetAttribute(pearson_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

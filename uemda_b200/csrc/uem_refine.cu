@@ -25,7 +25,6 @@
 //     table updated with one atomicMax per class per CTA.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
-#include <stdlib.h>
 
 int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, const int64_t* index, int b, int64_t N,
                          int c, int64_t R, int op, const int64_t* hot_ptr, int64_t hot_val, int skip_hot, unsigned* table,
@@ -41,22 +40,10 @@ int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats
 #ifndef UEM_REFINE_MINB
 #define UEM_REFINE_MINB 4   // resident 128-thread CTAs per SM the TMA kernel is compiled for (register cap = 64K/(128*MINB))
 #endif
-#ifndef UEM_REFINE_EXP
-#define UEM_REFINE_EXP 0    // development experiments: 1 = no soft/id loads (compute floor), 2 = no view math (memory floor)
-#endif
 
-#ifndef UEM_NO_PACKED
-#define UEM_NO_PACKED 0     // development experiment: 1 = scalar FFMA/FMUL/FADD instead of the packed fp32x2 forms
-#endif
-#if UEM_NO_PACKED
-#define UEM_FFMA2(a, b, c) make_float2(fmaf((a).x, (b).x, (c).x), fmaf((a).y, (b).y, (c).y))
-#define UEM_FMUL2(a, b) make_float2((a).x * (b).x, (a).y * (b).y)
-#define UEM_FADD2(a, b) make_float2((a).x + (b).x, (a).y + (b).y)
-#else
 #define UEM_FFMA2(a, b, c) __ffma2_rn(a, b, c)
 #define UEM_FMUL2(a, b) __fmul2_rn(a, b)
 #define UEM_FADD2(a, b) __fadd2_rn(a, b)
-#endif
 
 namespace {
 
@@ -480,7 +467,6 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
         const int y = (int)(rr - (int64_t)bi * H);
         unsigned char* dst = smem_raw + (size_t)stage * L.stage_bytes;
         const float* src = p.soft + (int64_t)bi * C * HW + (int64_t)y * W;
-        if (UEM_REFINE_EXP == 1) return;
         mbar_arrive_expect_tx(&full[stage], L.stage_bytes);
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) tma_load_1d(dst + (size_t)ci * W * 4, src + (int64_t)ci * HW, (uint32_t)W * 4u, &full[stage]);
@@ -584,7 +570,7 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
         if (ny == H) { ny = 0; ++nbi; }
         const bool has_next = it + 1 < nrows;
         if (has_next) fetch_lowres(nbi, ny);
-        if (UEM_REFINE_EXP != 1) mbar_wait(&full[stage], parity);  // this row's soft planes + ids have landed (issued NSTAGE rows ago)
+        mbar_wait(&full[stage], parity);  // this row's soft planes + ids have landed (issued NSTAGE rows ago)
 
         const float* soft_s = reinterpret_cast<const float*>(smem_raw + (size_t)stage * L.stage_bytes);
         const longlong2* ids_s = reinterpret_cast<const longlong2*>(soft_s + (size_t)C * W);
@@ -617,12 +603,6 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
             }
             const float* col = row + col_off;
             float2 wgt2[PC][4];
-#if UEM_REFINE_EXP == 2
-#pragma unroll
-            for (int j = 0; j < PC; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) wgt2[j][i] = make_float2(wa[i] + col[0], wb[i]);
-#else
             {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
                 float2 t[3][PC];
                 load_tap3p<C>(col, STRIDE, t);
@@ -669,7 +649,6 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
                     for (int j = 0; j < PC; ++j) wgt2[j][i] = UEM_FFMA2(z[j], inv2, wgt2[j][i]);
                 }
             }
-#endif
             // superpixel view: multiplicative outside the ignored id (branch-free: the ignored id and any id outside
             // [0,R) are redirected to the all-ones sentinel row R)
             {
@@ -928,8 +907,7 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
         bool done = false;
-        static const bool pdl_enabled = !(getenv("UEM_PDL") && getenv("UEM_PDL")[0] == '0');  // development switch
-        if (fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0 && pdl_enabled, &done);
+        if (fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0, &done);
         if (!done && rc == 0) {
             const int vecw = vec ? 4 : 1;
             const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
