@@ -67,18 +67,19 @@ __global__ void __launch_bounds__(256) logits_pass_kernel(const float* __restric
 #pragma unroll
                 for (int ci = 0; ci < C; ++ci) acc[ci] += z[ci];
             }
-            float best = -INFINITY, e = 0.f;
+            float best = -INFINITY;
             int arg = 0;
+            float pp[C];
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
                 float v = (nmaps == 2) ? acc[ci] * 0.5f : acc[ci];
                 p[ci][i] = v;
+                pp[ci] = v;
                 bool gt = v > best;
                 best = gt ? v : best;
                 arg = gt ? ci : arg;
-                e += (-v) * logf(v);  // balance.py:372; p==0 -> NaN like the reference
             }
-            cf[i] = best; en[i] = e; am[i] = arg;
+            cf[i] = best; en[i] = entropy_px<C>(pp); am[i] = arg;  // balance.py:372; p==0 -> NaN like the reference
         }
         const int64_t px = (int64_t)y * W + x0;
         if (soft) {
