@@ -174,8 +174,10 @@ def run_reference_arm(args, wl):
         "impl": "reference", "metric": "pseudo-label mining throughput", "value": val, "unit": "Mpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.name, "b": wl.b, "c": wl.c, "H": wl.H, "W": wl.W, "k": wl.k, "feat_scale": wl.scale,
-                   "regions": wl.regions},
+        "config": {"workload": wl.name, "b_per_gpu": wl.b, "c": wl.c, "H": wl.H, "W": wl.W, "k": wl.k, "feat_scale": wl.scale,
+                   "regions": wl.regions, "step": "label_refine(all)+pseudo_selection+update_prototype+entropy/uvem_weight",
+                   "l2_policy": "n/a (host cores)", "cuda_graph": False,
+                   "parallelism": "rank 0 only, %d host threads" % torch.get_num_threads()},
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d of %d images per step" % (n_img, wl.b)},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

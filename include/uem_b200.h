@@ -227,6 +227,21 @@ UEM_API int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float hi
  * uint8(label + 1), i.e. ignore (-1) -> 0, class j -> j+1 (numpy astype semantics: modulo 256). */
 UEM_API int uem_label_plus1_u8_i64(const int64_t* label, int64_t n, uint8_t* out, void* stream);
 
+/* ---- PrototypeContrastiveLoss, forward + backward (next row) ---------------------
+ * uemda/loss.py:10-47 (tools/train_align_uem.py:176-177): loss = mean over non-ignored pixels of
+ * CrossEntropy(normalize(f) normalize(P)^T / T, label).  feat (b,k,hw) planar NCHW read in place (hw % 4 == 0,
+ * k >= 32), protos (c,k), labels (b,hw) int64.
+ * forward : loss[0] (NaN if no pixel is valid, like the reference) and coef (b, c+1, hw): the per-pixel backward
+ *           coefficients a_j = (softmax_j - onehot_j) / (Nv T ||f||), beta = sum_j a_j (f.P^_j) / ||f||^2.
+ * backward: grad_feat (b,k,hw) = grad_out[0] * (sum_j a_j P^_j[k] - beta f[k]); grad_out: device scalar or NULL (= 1).
+ * ws: uem_pcl_ws_bytes(b,k,hw), the same buffer for both calls (it keeps the normalised prototypes). */
+UEM_API int64_t uem_pcl_ws_bytes(int b, int k, int64_t hw);
+UEM_API int uem_pcl_forward_f32(const float* feat, int b, int k, int64_t hw, const float* protos, int c,
+                        const int64_t* labels, int64_t ignore_label, float temperature, float* loss,
+                        float* coef, void* ws, void* stream);
+UEM_API int uem_pcl_backward_f32(const float* feat, int b, int k, int64_t hw, int c, const float* coef,
+                         const float* grad_out, float* grad_feat, const void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -371,3 +371,21 @@ def mining_step(inp, prototypes, class_num, mode="all", temp=2.0, cutoff_top=0.8
     u = entropy(refined)
     out.update(entropy=u, uvem_weight=uvem_weight(u, *uvem))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# next row 8f-2: PrototypeContrastiveLoss (uemda/loss.py:18-47), autograd supplies the backward
+# --------------------------------------------------------------------------------------
+def pcl_loss(protos, feat, labels, temperature=8.0, ignore_label=-1):
+    """feat (b,k,h,w) or (N,k) with requires_grad; returns the scalar loss (call .backward() for d/dfeat)."""
+    if feat.dim() != 2:
+        k = feat.size(1)
+        feat = feat.permute(0, 2, 3, 1).reshape(-1, k)      # loss.py:30-31
+    labels = labels.reshape(-1)                             # :32-33
+    mask = labels != ignore_label                            # :36-38
+    labels = labels[mask]
+    feat = feat[mask]
+    feat = F.normalize(feat, p=2, dim=1)                     # :40-41
+    protos = F.normalize(protos, p=2, dim=1)
+    logits = feat.mm(protos.permute(1, 0).contiguous()) / temperature   # :43-44
+    return F.cross_entropy(logits, labels)                   # :46

@@ -493,3 +493,54 @@ def test_fused_fold_finalize_equals_two_step(dev):
     state = d["prototypes"].clone()
     ops.proto_fold_finalize(part, state, decay=0.996, out=state)
     _eq(state, want, "in-place fused fold + finalize")
+
+
+# ------------------------------------------------------------------------------------ next row 8f-2: PCL loss
+def test_pcl_loss_golden_forward_backward(dev):
+    """PrototypeContrastiveLoss forward + backward against the reference's own outputs (tests/golden/pcl_small.npz)."""
+    import os
+    from uemda_b200.loss import PrototypeContrastiveLoss
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pcl_small.npz"))
+    protos = torch.from_numpy(z["in_protos"]).to(dev)
+    labels = torch.from_numpy(z["in_labels"]).to(dev)
+    for temp in (8.0, 0.5):
+        f = torch.from_numpy(z["in_feat"]).to(dev).requires_grad_(True)
+        loss = PrototypeContrastiveLoss(temperature=temp, ignore_label=-1)(protos, f, labels)
+        (loss * 1.0).backward()
+        assert_close(loss.detach().reshape(1), torch.from_numpy(z["out_loss_t%g" % temp]).reshape(1), rtol=RTOL, atol=1e-7, what="pcl loss")
+        assert_close(f.grad, torch.from_numpy(z["out_grad_t%g" % temp]), rtol=1e-4, atol=1e-7, what="pcl grad")
+
+
+def test_pcl_loss_vs_oracle_config_shape(dev):
+    """Config-2 feature shape (8,2048,32,32): loss and gradient vs the oracle's autograd; upstream gradient scaling;
+    the (N,A) row form; all-ignored labels give NaN like the reference's mean over an empty set."""
+    from oracle import uem_oracle as O
+    from uemda_b200.loss import PrototypeContrastiveLoss
+    g = torch.Generator().manual_seed(5)
+    b, k, h, w, c = 8, 2048, 32, 32, 6
+    protos = torch.randn(c, k, generator=g)
+    lab = torch.randint(-1, c, (b, 1, h, w), generator=g)
+    feat = torch.randn(b, k, h, w, generator=g) + 0.5 * protos[lab.clamp(min=0).squeeze(1)].permute(0, 3, 1, 2)
+    f_ref = feat.clone().requires_grad_(True)
+    want = O.pcl_loss(protos, f_ref, lab, temperature=8.0)
+    (want * 0.5).backward()
+    fn = PrototypeContrastiveLoss(temperature=8.0, ignore_label=-1)
+    f = feat.to(dev).requires_grad_(True)
+    loss = fn(protos.to(dev), f, lab.to(dev))
+    (loss * 0.5).backward()
+    assert_close(loss.detach().reshape(1), want.detach().reshape(1), rtol=RTOL, atol=1e-7, what="pcl loss cfg2")
+    scale = float(f_ref.grad.abs().max())
+    assert_close(f.grad, f_ref.grad, rtol=1e-4, atol=1e-5 * scale, what="pcl grad cfg2")
+    # (N, A) rows
+    rows = feat.permute(0, 2, 3, 1).reshape(-1, k)[:1000].contiguous()
+    r_ref = rows.clone().requires_grad_(True)
+    w2 = O.pcl_loss(protos, r_ref, lab.reshape(-1)[:1000], temperature=8.0)
+    w2.backward()
+    r = rows.to(dev).requires_grad_(True)
+    l2 = fn(protos.to(dev), r, lab.reshape(-1)[:1000].to(dev))
+    l2.backward()
+    assert_close(l2.detach().reshape(1), w2.detach().reshape(1), rtol=RTOL, atol=1e-7, what="pcl loss rows")
+    assert_close(r.grad, r_ref.grad, rtol=1e-4, atol=1e-5 * float(r_ref.grad.abs().max()), what="pcl grad rows")
+    # nothing valid -> NaN (CrossEntropyLoss mean over zero elements)
+    f3 = feat[:1].to(dev).requires_grad_(True)
+    assert torch.isnan(fn(protos.to(dev), f3, torch.full((1, 1, h, w), -1, device=dev)))

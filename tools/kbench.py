@@ -66,6 +66,9 @@ def main():
         "superpixel_expand": (lambda s: ops.superpixel_expand(s["hard"], s["sup"], c, num_regions=R), P * 24),
         "class_hist": (lambda s: ops.class_hist(s["hard"], c), P * 8),
         "logits_pass": (lambda s: ops.softmax_conf_entropy_argmax(s["pred1"], s["pred2"], size=(wl.H, wl.W)), P * (4 * c + 16)),
+        "pcl_forward": (lambda s: ops.pcl_forward(s["feat_s"], protos, s["down"], 8.0), feat_bytes),
+        "pcl_fwd+bwd": (lambda s: (lambda o: ops.pcl_backward(s["feat_s"], o[1], o[2]))(ops.pcl_forward(s["feat_s"], protos, s["down"], 8.0)),
+                        3 * feat_bytes),
         "mine_chain": (lambda s: mining.refine_select(7, s["soft"], 2.0, feat=s["feat"], prototypes=protos, pred1=s["pred1"],
                                                       pred2=s["pred2"], sup=s["sup"], num_regions=R, select=(0.8, 0.6, -1),
                                                       ws=ws, uvem=(0.2, 0.7, 4.0)),

@@ -408,3 +408,35 @@ def label_plus1_u8(label):
     out = torch.empty(label.shape, dtype=torch.uint8, device=label.device)
     L.check(lib.uem_label_plus1_u8_i64(L.ptr(label), label.numel(), L.ptr(out), L.stream_of(label)))
     return out
+
+
+# --------------------------------------------------------------------------------------------- PCL loss (8f-2)
+def pcl_forward(feat, prototypes, labels, temperature=8.0, ignore_label=-1):
+    """uemda/loss.py:18-47 on an NCHW feature map read in place. Returns (loss (1,), coef (b,c+1,h*w), ws)."""
+    L.require_cuda(feat, prototypes, labels)
+    feat = L.f32c(feat.detach())
+    protos = L.f32c(prototypes.detach())
+    labels = L.i64c(labels.detach())
+    b, k, h, w = feat.shape
+    c = protos.shape[0]
+    assert protos.shape[1] == k and labels.numel() == b * h * w
+    lib = L.bind(feat)
+    loss = torch.empty(1, dtype=torch.float32, device=feat.device)
+    coef = torch.empty((b, c + 1, h * w), dtype=torch.float32, device=feat.device)
+    ws = L.workspace(lib.uem_pcl_ws_bytes(b, k, h * w), feat)
+    L.check(lib.uem_pcl_forward_f32(L.ptr(feat), b, k, h * w, L.ptr(protos), c, L.ptr(labels), int(ignore_label), f32(temperature),
+                                    L.ptr(loss), L.ptr(coef), L.ptr(ws), L.stream_of(feat)))
+    return loss, coef, ws
+
+
+def pcl_backward(feat, coef, ws, grad_out=None):
+    """d loss / d feat (b,k,h,w) from the coefficients of pcl_forward."""
+    L.require_cuda(feat, coef, ws, grad_out)
+    feat = L.f32c(feat.detach())
+    b, k, h, w = feat.shape
+    c = coef.shape[1] - 1
+    lib = L.bind(feat)
+    grad = torch.empty_like(feat)
+    g = None if grad_out is None else L.f32c(grad_out.detach()).reshape(1)
+    L.check(lib.uem_pcl_backward_f32(L.ptr(feat), b, k, h * w, c, L.ptr(coef), L.ptr(g), L.ptr(grad), L.ptr(ws), L.stream_of(feat)))
+    return grad
