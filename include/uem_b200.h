@@ -142,8 +142,9 @@ UEM_API int uem_downscale_label_i64(const int64_t* label, int b, int H, int W, i
  * nchw: feat (b,k,hw) planar, protos (m,k) row-major -> out (b,m,hw) planar:
  *   out = dist, or 1/dist if reciprocal!=0 (alignment.py:216).  m <= UEM_MAX_CLASSES.
  * rows: feat1 (n,k), feat2 (m,k) row-major -> out (n,m) row-major, any m.
- * ws: uem_pearson_ws_bytes(m,k). */
+ * ws: uem_pearson_nchw_ws_bytes(b,hw,m,k) for the nchw form, uem_pearson_ws_bytes(m,k) for the rows form. */
 UEM_API int64_t uem_pearson_ws_bytes(int m, int k);
+UEM_API int64_t uem_pearson_nchw_ws_bytes(int b, int64_t hw, int m, int k);
 UEM_API int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_t hw, const float* protos, int m,
                               float eps, int reciprocal, float* out, void* ws, void* stream);
 UEM_API int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, const float* feat2, int m,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "uem_superpixel_expand_i64": (_I, [_P, _P, _I, _L, _I, _L, _L, _P, _P, _P]),
     "uem_downscale_label_i64": (_I, [_P, _I, _I, _I, _I, _I, _L, _F, _P, _P, _P]),
     "uem_pearson_ws_bytes": (_L, [_I, _I]),
+    "uem_pearson_nchw_ws_bytes": (_L, [_I, _L, _I, _I]),
     "uem_pearson_dist_nchw_f32": (_I, [_P, _I, _I, _L, _P, _I, _F, _I, _P, _P, _P]),
     "uem_pearson_dist_rows_f32": (_I, [_P, _L, _I, _P, _I, _F, _P, _P, _P]),
     "uem_label_refine_ws_bytes": (_L, [_I, _I, _L, _I]),

@@ -10,8 +10,6 @@
 // the residual mean(g)*sum(pc_j) is subtracted anyway).  HBM-bound on feat: 4k B per feature pixel.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -23,8 +21,11 @@ constexpr int kPcStride = 8;   // transposed centred prototypes: pcT[kk][8] -> t
 
 // centre the prototypes once: pc (m,k), stats[j] = {std_j (unbiased), sum_k pc_j}
 __global__ void __launch_bounds__(256) proto_center_kernel(const float* __restrict__ protos, int k, int transposed,
-                                                           float* __restrict__ pc, float* __restrict__ stats) {
+                                                           float* __restrict__ pc, float* __restrict__ stats,
+                                                           int* __restrict__ zero_ints, int n_zero) {
     const int j = blockIdx.x;
+    if (j == 0)  // arrival counters of the k-split fold (uninitialised caller workspace)
+        for (int i = threadIdx.x; i < n_zero; i += 256) zero_ints[i] = 0;
     const float* p = protos + (int64_t)j * k;
     __shared__ float red[8];
     __shared__ float bc;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(kPearsonThreads, 4) pearson_nchw_kernel(const 
 // TMA form (hw % 4 == 0): the NCHW map is streamed as [kKT channels x kPT pixels] tiles (cp.async.bulk.tensor,
 // 16 KB each) through a kStages-deep mbarrier ring filled by a dedicated producer warp; 8 consumer warps keep the
 // 2+M running sums of their 4 pixels in registers (packed FFMA2 over pixel pairs, the centred prototype as the
-// scalar operand).  The k dimension is split over the CTAs of a thread-block cluster; the partial sums are
-// combined through distributed shared memory (no global scratch, no atomics) and rank 0 finishes the distance.
+// scalar operand).  The k dimension is split over KS CTAs per pixel tile; their partial sums meet in an L2-resident
+// scratch array and the last CTA to arrive adds them in split order (deterministic) and finishes the distance.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPT = 128;      // pixels per tile (512 B rows)
 constexpr int kKT = 32;       // channels per tile
@@ -198,8 +199,9 @@ constexpr int kTmaThreads = kConsumers + 32;
 
 template <int M>
 __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ feat,
-                                                                  int k, int hw, int kper, const float* __restrict__ pc,
+                                                                  int k, int hw, int kper, int KS, const float* __restrict__ pc,
                                                                   const float* __restrict__ stats, float eps, int reciprocal,
+                                                                  float* __restrict__ gpart, int* __restrict__ arrivals,
                                                                   float* __restrict__ out) {
     constexpr int NA = 2 + M;
     extern __shared__ __align__(128) unsigned char smem_p[];
@@ -207,9 +209,9 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
     float* pcs = tiles + (size_t)kStages * kKT * kPT;                                  // [kStages][kKT][kPcStride] centred prototypes
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_p + (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4);
     uint64_t* empty = full + kStages;
-    float* part = reinterpret_cast<float*>(empty + kStages);                           // [NA][kPT] CTA partial (cluster-visible)
-    cg::cluster_group cluster = cg::this_cluster();
-    const int ks = (int)cluster.block_rank(), KS = (int)cluster.num_blocks();
+    float* part = reinterpret_cast<float*>(empty + kStages);                           // [NA][kPT] CTA partial
+    __shared__ int s_last;
+    const int ks = blockIdx.x % KS;
     const int ptile = blockIdx.x / KS, bi = blockIdx.y;
     const int px0 = ptile * kPT;
     const int kbeg = ks * kper, kend = min(k, kbeg + kper);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
                 tma_load_1d(pcs + (size_t)s * kKT * kPcStride, pc + (int64_t)kk0 * kPcStride, pc_bytes, &full[s]);
             }
         }
-        __syncwarp();  // the warp re-converges before the (aligned) cluster barrier below
+        __syncwarp();
     } else {
         // ---- consumers: warp -> channels warp, warp+8, .. of the tile; lane -> 4 consecutive pixels
         const int px = px0 + lane * 4;
@@ -302,17 +304,36 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
             }
         }
     }
-    // ---- fold the k splits across the cluster through distributed shared memory; rank 0 finishes
-    cluster.sync();
-    if (ks == 0 && threadIdx.x < kPT) {
+    // ---- fold the k splits: every CTA parks its partial sums in global memory (L2), the last one to arrive for this
+    // (image, pixel tile) adds them in split order (deterministic) and finishes the distance.  (A thread-block cluster
+    // with a DSMEM fold measured slower: the cluster barrier holds every CTA until the slowest of the group is done.)
+    __syncthreads();
+    float* mine = gpart + ((size_t)(blockIdx.y * (gridDim.x / KS) + ptile) * KS) * NA * kPT;
+    if (KS > 1) {
+        if (threadIdx.x < kPT) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) mine[((size_t)ks * NA + a) * kPT + threadIdx.x] = part[a * kPT + threadIdx.x];
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(arrivals + blockIdx.y * (gridDim.x / KS) + ptile, 1) == KS - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
+    if (threadIdx.x < kPT) {
         const int px = px0 + threadIdx.x;
         float sacc[NA];
+        if (KS > 1) {
 #pragma unroll
-        for (int a = 0; a < NA; ++a) sacc[a] = part[a * kPT + threadIdx.x];
-        for (int r = 1; r < KS; ++r) {
-            const float* rp = cluster.map_shared_rank(part, r);
+            for (int a = 0; a < NA; ++a) sacc[a] = 0.f;
+            for (int r = 0; r < KS; ++r) {
 #pragma unroll
-            for (int a = 0; a < NA; ++a) sacc[a] += rp[a * kPT + threadIdx.x];
+                for (int a = 0; a < NA; ++a) sacc[a] += __ldcg(mine + ((size_t)r * NA + a) * kPT + threadIdx.x);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) sacc[a] = part[a * kPT + threadIdx.x];
         }
         if (px < hw) {
 #pragma unroll
@@ -321,7 +342,7 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
                     pearson_finish(sacc[0], sacc[1], sacc[2 + j], stats[2 * j], stats[2 * j + 1], k, eps, reciprocal);
         }
     }
-    cluster.sync();  // remote partials stay alive until rank 0 has read them
+    if (KS > 1 && threadIdx.x == 0) arrivals[blockIdx.y * (gridDim.x / KS) + ptile] = 0;  // clean for the next call
 }
 
 // generic row-major (n,k) x (m,k): one warp per feat1 row, classes in chunks of 8
@@ -366,42 +387,50 @@ extern "C" int64_t uem_pearson_ws_bytes(int m, int k) {
     return (rows * k + 2 * (int64_t)m + 4) * sizeof(float);
 }
 
+// k split of the TMA kernel: at most ~2 CTAs per SM (all resident at once), each with at least 4 tiles of its own
+static int pearson_ksplit(int b, int64_t hw, int k) {
+    const int ptiles = uem_div_up(hw, kPT);
+    int KS = 1;
+    while (KS < 8 && (int64_t)ptiles * b * KS * 2 <= 2 * UEM_SMS && k / (KS * 2) >= 4 * kKT) KS *= 2;
+    return KS;
+}
+
+// NCHW entry: [pc k*8 f32][stats 2*m f32 (+pad)][arrival counters b*ptiles i32][k-split partial sums]
+extern "C" int64_t uem_pearson_nchw_ws_bytes(int b, int64_t hw, int m, int k) {
+    const int64_t ptiles = (hw + kPT - 1) / kPT;
+    const int KS = pearson_ksplit(b, hw, k);
+    int64_t n = ((int64_t)kPcStride * k + 2 * (int64_t)m + 4) * 4;
+    n = (n + 15) & ~(int64_t)15;
+    n += ((int64_t)b * ptiles * 4 + 15) & ~(int64_t)15;
+    n += (KS > 1) ? (int64_t)b * ptiles * KS * (2 + m) * kPT * 4 : 0;
+    return n;
+}
+
 extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_t hw, const float* protos, int m, float eps,
                                          int reciprocal, float* out, void* ws, void* stream) {
     UEM_REQUIRE(feat && protos && out && ws && b > 0 && k > 0 && hw > 0, "uem_pearson_dist_nchw_f32: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     float* pc = (float*)ws;
     float* stats = pc + (int64_t)kPcStride * k;
+    const int64_t ptiles64 = (hw + kPT - 1) / kPT;
+    int* arrivals = (int*)((char*)ws + ((((int64_t)kPcStride * k + 2 * (int64_t)m + 4) * 4 + 15) & ~(int64_t)15));
+    float* gpart = (float*)((char*)arrivals + (((int64_t)b * ptiles64 * 4 + 15) & ~(int64_t)15));
     const bool vec = (hw % 4 == 0) && uem_aligned16(feat);
     const bool tma = vec && hw < (1 << 30) && k >= kKT;
     UEM_DISPATCH_C(m, {
-        proto_center_kernel<<<C, 256, 0, st>>>(protos, k, 1, pc, stats);
+        proto_center_kernel<<<C, 256, 0, st>>>(protos, k, 1, pc, stats, arrivals, tma ? (int)(b * ptiles64) : 0);
         if (tma) {
             CUtensorMap tmap;
             UEM_REQUIRE(uem_make_tmap_3d_f32(&tmap, feat, (uint64_t)hw, (uint64_t)k, (uint64_t)b, (uint64_t)hw, (uint64_t)k * hw, kPT,
                                              kKT) == 0,
                         "uem_pearson_dist_nchw_f32: cuTensorMapEncodeTiled failed");
             const int ptiles = uem_div_up(hw, kPT);
-            // split k over a cluster so that ~2 CTAs per SM are busy, each with at least 4 tiles of its own
-            int KS = 1;
-            while (KS < 8 && (int64_t)ptiles * b * KS * 2 <= 2 * UEM_SMS && k / (KS * 2) >= 4 * kKT) KS *= 2;
+            const int KS = pearson_ksplit(b, hw, k);
             const int kper = ((k + KS - 1) / KS + kKT - 1) / kKT * kKT;
             const size_t smem = (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4 + 2 * kStages * 8 + (size_t)kPT * (2 + C) * 4;
             UEM_CUDA(cudaFuncSetAttribute(pearson_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ptiles * KS, b, 1);
-            cfg.blockDim = dim3(kTmaThreads, 1, 1);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = KS;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            UEM_CUDA(cudaLaunchKernelEx(&cfg, pearson_tma_kernel<C>, tmap, feat, k, (int)hw, kper, (const float*)pc, (const float*)stats,
-                                        eps, reciprocal, out));
+            pearson_tma_kernel<C><<<dim3(ptiles * KS, b), kTmaThreads, smem, st>>>(tmap, feat, k, (int)hw, kper, KS, pc, stats, eps, reciprocal,
+                                                                                   gpart, arrivals, out);
         } else if (vec) {
             dim3 grid(uem_div_up(hw, kPxLanes * 4), b);
             pearson_nchw_kernel<C, 4><<<grid, kPearsonThreads, 0, st>>>(feat, k, hw, pc, stats, eps, reciprocal, out);
@@ -420,7 +449,7 @@ extern "C" int uem_pearson_dist_rows_f32(const float* feat1, int64_t n, int k, c
     cudaStream_t st = (cudaStream_t)stream;
     float* pc = (float*)ws;
     float* stats = pc + (int64_t)(m > kPcStride ? m : kPcStride) * k;
-    proto_center_kernel<<<m, 256, 0, st>>>(feat2, k, 0, pc, stats);
+    proto_center_kernel<<<m, 256, 0, st>>>(feat2, k, 0, pc, stats, nullptr, 0);
     pearson_rows_kernel<<<uem_div_up(n, 8), 256, 0, st>>>(feat1, n, k, pc, stats, m, eps, out);
     UEM_CHECK_LAUNCH_N(2);
     return 0;

@@ -982,7 +982,7 @@ static MineLayout mine_layout(int b, int c, int W, int h, int w, int k, int64_t 
     L.region = n; n += align16((int64_t)b * R * c * 4);
     L.zero_end = n;
     L.simi = n; n += align16((int64_t)b * c * h * w * 4);
-    L.pearson = n; n += align16(uem_pearson_ws_bytes(c, k));
+    L.pearson = n; n += align16(uem_pearson_nchw_ws_bytes(b, (int64_t)h * w, c, k));
     L.sw = n; n += uem_label_refine_ws_bytes(b, c, R, W);
     L.end = n;
     return L;

@@ -251,7 +251,7 @@ def pearson_dist_nchw(feat, prototypes, eps=1e-7, reciprocal=False):
     assert protos.shape[1] == k
     lib = L.bind(feat)
     out = torch.empty((b, m, h, w), dtype=torch.float32, device=feat.device)
-    ws = L.workspace(lib.uem_pearson_ws_bytes(m, k), feat)
+    ws = L.workspace(lib.uem_pearson_nchw_ws_bytes(b, h * w, m, k), feat)
     L.check(lib.uem_pearson_dist_nchw_f32(L.ptr(feat), b, k, h * w, L.ptr(protos), m, f32(eps), int(reciprocal), L.ptr(out),
                                           L.ptr(ws), L.stream_of(feat)))
     return out
