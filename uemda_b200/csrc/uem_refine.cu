@@ -104,12 +104,12 @@ template <int PC> __device__ __forceinline__ float exp2_shifted2(float2 (&z)[PC]
 #pragma unroll
     for (int j = 1; j < PC; ++j) mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
     const float2 nmx = make_float2(-mx, -mx);
-    float2 acc = make_float2(0.f, 0.f);
+    float2 acc;
 #pragma unroll
     for (int j = 0; j < PC; ++j) {
         const float2 d = UEM_FADD2(z[j], nmx);
         z[j] = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-        acc = UEM_FADD2(acc, z[j]);
+        acc = j ? UEM_FADD2(acc, z[j]) : z[j];
     }
     return acc.x + acc.y;
 }
@@ -710,6 +710,290 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
     if (p.stats) flush_stats<C>(p.stats, bi - (y == 0 ? 1 : 0), cmax, cmin, bad, red);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column-walk kernel (default configuration: all three views, two heads, W % 4 == 0).
+// A thread owns ONE image column of a strip of NT columns and walks down a contiguous range of rows, so everything
+// that depends on the column only is hoisted out of the row loop:
+//   * the horizontal half of the bilinear interpolation is done once per low-res row pair (every ~H/h output rows):
+//     A_c = lerp_x(map[i0]), B_c = lerp_x(map[i1]) for the 3C (map, class) planes, kept in registers as
+//     A' = kappa*A and D' = kappa*(B - A) (kappa = log2 e [/temp]); per output row the interpolated, pre-scaled
+//     logit is ONE packed FFMA per class pair: z' = A' + t_y * D', and the softmax exponent is a bare EX2;
+//   * no tap row in shared memory, no per-row vertical interpolation pass, and NO barrier of any kind in the row
+//     loop: every thread copies its own 4C+8 bytes of a row (C soft planes + the superpixel id) global -> shared
+//     with cp.async (LDGSTS, 128 contiguous bytes per warp and plane), NS-1 rows ahead, and reads back only what it
+//     copied itself, so cp.async.wait_group is the only synchronisation (a first version that fed NT-column strips
+//     with 512-byte cp.async.bulk copies was bound by the per-copy cost of the TMA unit: 66 us);
+//   * the global stores are 32-bit per lane, contiguous over the warp (full 128-byte lines), class maps stay planar.
+// 1 pixel per thread keeps the state at 6*PC registers + temporaries, so 5 CTAs of 128 threads are resident per SM.
+// ------------------------------------------------------------------------------------------------
+#ifndef UEM_REFINE_COL_MINB
+#define UEM_REFINE_COL_MINB 4   // 128 registers: no spills for C <= 8 (5 resident CTAs spill and run 30% slower at C = 7)
+#endif
+
+template <int C, int NT, int NS>
+__global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_col_kernel(const RefineParams p, const int ncols_max) {
+    constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32;
+    constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
+    constexpr uint32_t kWarpStage = 32u * (4u * C + 8u);         // bytes of one row of a warp's 32 columns
+    constexpr int NCHUNK = 8 * C + 16;                           // 16-byte chunks of it: 8 per soft plane + 16 of ids
+    constexpr int NCP = (NCHUNK + 31) / 32;                      // cp.async per lane and row
+    extern __shared__ __align__(128) unsigned char smem_col[];
+    const int W = p.W, H = p.H, w = p.w, h = p.h;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t HW = (int64_t)H * W;
+    const int hw_low = h * w;
+    const int nstrips = (W + NT - 1) / NT;
+    // shared memory: [warp][stage][C planes x 32 floats | 32 ids]  then  [warp][2 rows][ncols_max][TS] tap scratch
+    unsigned char* const wstage = smem_col + (size_t)wid * NS * kWarpStage;
+    float* const taps = reinterpret_cast<float*>(smem_col + (size_t)NW * NS * kWarpStage) + (size_t)wid * 2 * ncols_max * TS;
+
+    // flattened (image, strip, row) space, row fastest; this CTA owns [U0, U1)
+    const int64_t total = (int64_t)p.b * nstrips * H;
+    const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int n = (int)(U1 - U0);
+    if (n <= 0) return;
+    const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
+
+    // ---- prefetch side.  A row of the warp's 32 columns is NCHUNK 16-byte chunks (chunk k sits at byte 16k of the
+    // stage: planes are 128 bytes each, ids follow); lane l copies chunks l, l+32[, l+64] with cp.async.cg 16.
+    // The source pointer of each chunk advances by one image row per unit; recomputed when the strip changes.
+    const uint32_t wstage_u32 = smem_u32(wstage) + (uint32_t)lane * 16u;
+    const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * 4u;
+    int ibs = bs0, iy = y0, ibs_cur = -1;
+    const char* csrc[NCP];
+    uint32_t cstride[NCP];
+    bool cvalid[NCP];
+#pragma unroll
+    for (int q = 0; q < NCP; ++q) { csrc[q] = nullptr; cstride[q] = 0; cvalid[q] = false; }
+    auto prefetch = [&](int stage) {
+        if (ibs != ibs_cur) {
+            const int bi = ibs / nstrips, s = ibs - bi * nstrips;
+            const int xw = s * NT + wid * 32;
+#pragma unroll
+            for (int q = 0; q < NCP; ++q) {
+                const int k = lane + 32 * q;
+                if (k < 8 * C) {
+                    const int ci = k >> 3, x = xw + (k & 7) * 4;
+                    cvalid[q] = x < W;
+                    csrc[q] = reinterpret_cast<const char*>(p.soft + ((int64_t)bi * C + ci) * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
+                    cstride[q] = (uint32_t)W * 4u;
+                } else {
+                    const int x = xw + (k - 8 * C) * 2;
+                    cvalid[q] = (k < NCHUNK) && x < W;
+                    csrc[q] = reinterpret_cast<const char*>(p.sup + (int64_t)bi * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
+                    cstride[q] = (uint32_t)W * 8u;
+                }
+            }
+            ibs_cur = ibs;
+        }
+        const uint32_t d = wstage_u32 + (uint32_t)stage * kWarpStage;
+#pragma unroll
+        for (int q = 0; q < NCP; ++q) {
+            if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            csrc[q] += cstride[q];
+        }
+        if (++iy == H) { iy = 0; ++ibs; }
+    };
+#pragma unroll
+    for (int s = 0; s < NS - 1; ++s) {   // inputs only: safe before the dependency wait
+        if (s < n) prefetch(s);
+        cp_async_commit_group();
+    }
+    // programmatic dependent launch: the similarity map, the region weights and the ignored id come from the
+    // preceding kernels; everything above touched this kernel's inputs and its own shared memory only
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int64_t ignored_id = *p.ignored_id;
+    const uint32_t ign_lo = ((uint64_t)ignored_id >> 32) == 0 ? (uint32_t)ignored_id : 0xffffffffu;
+    const uint32_t Ru = (uint32_t)p.R;
+
+    // column state: pre-scaled row-pair interpolants of the three maps (pairs of classes; padded slot -> e = 0)
+    float2 A[3][PC], D[3][PC];
+    int cur_bs = -1, cur_i0 = -1, cur_b = -1;
+    int a0 = 0, a1 = 0, abase = 0, ncols = 1;
+    float l0x = 0.f, l1x = 0.f;
+    bool active = false;
+    const float* ob = nullptr;      // out + (bi*C)*HW
+    uint32_t x = 0;
+    const float4* swb = nullptr;
+
+    float cmax[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) cmax[ci] = -INFINITY;
+    float cmin = INFINITY, nanacc = 0.f;
+
+    auto flush = [&](int bi) {      // per warp: shuffle-reduce, one atomic per statistic
+        float mn = warp_min(cmin);
+        const int anybad = __any_sync(0xffffffffu, nanacc != nanacc);
+        float mine = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const float v = warp_max(cmax[ci]);
+            if (lane == ci) mine = v;
+            cmax[ci] = -INFINITY;
+        }
+        unsigned* srow = p.stats + (int64_t)bi * (C + 2);
+        if (lane < C) { if (mine > -INFINITY) atomicMax(srow + lane, f32_to_ordered(mine)); }
+        else if (lane == C) { if (mn < INFINITY) atomicMax(srow + C, f32_to_ordered(-mn)); }
+        else if (lane == C + 1) { if (anybad) atomicOr(srow + C + 1, 1u); }
+        cmin = INFINITY;
+        nanacc = 0.f;
+    };
+
+    int bs = bs0, y = y0;
+    int stage = 0, pstage = NS - 1;
+    for (int it = 0; it < n; ++it) {
+        __syncwarp();                            // every lane is done with the stage row it-1 has just left
+        if (it + NS - 1 < n) prefetch(pstage);   // row it+NS-1 goes there
+        cp_async_commit_group();
+        if (bs != cur_bs) {        // new (image, strip): column geometry
+            const int bi = bs / nstrips, s = bs - bi * nstrips;
+            if (bi != cur_b) {
+                if (cur_b >= 0 && p.stats) flush(cur_b);
+                cur_b = bi;
+            }
+            const int xw = s * NT + wid * 32;
+            x = (uint32_t)(xw + lane);
+            active = (int)x < W;
+            const Lerp lx = make_lerp(active ? (int)x : W - 1, w, p.sx);
+            a0 = lx.i0; a1 = lx.i1; l0x = lx.l0; l1x = lx.l1;
+            abase = make_lerp(min(xw, W - 1), w, p.sx).i0;                 // warp-uniform: first low-res column
+            ncols = make_lerp(min(xw + 31, W - 1), w, p.sx).i1 - abase + 1;  // <= ncols_max
+            ob = p.out + (int64_t)bi * C * HW;
+            swb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
+            cur_bs = bs;
+            cur_i0 = -1;
+        }
+        const Lerp ly = make_lerp(y, h, p.sy);
+        if (ly.i0 != cur_i0) {
+            // new low-res row pair.  The warp's 32 columns span `ncols` low-res columns: their 2 x ncols x 3C values are
+            // fetched once per warp (lane -> (map, class)), pre-scaled by log2 e [/temp], and every lane then reads the
+            // four corners of its own column as 128-bit shared-memory loads and interpolates horizontally, once.
+            cur_i0 = ly.i0;
+            __syncwarp();
+            if (lane < 3 * C) {
+                const int m = lane / C, ci = lane - m * C;
+                const float* plane = p.maps[m] + ((int64_t)cur_b * C + ci) * hw_low + abase;
+                const float sc = p.map_scale[m];
+                float* dst = taps + m * CP + ci;
+                const float* r0 = plane + ly.i0 * w;
+                const float* r1 = plane + ly.i1 * w;
+                for (int j = 0; j < ncols; ++j) {
+                    dst[j * TS] = __ldg(r0 + j) * sc;
+                    dst[(ncols_max + j) * TS] = __ldg(r1 + j) * sc;
+                }
+            }
+            __syncwarp();
+            const float* t00 = taps + (a0 - abase) * TS;
+            const float* t01 = taps + (a1 - abase) * TS;
+            const float2 l0 = make_float2(l0x, l0x), l1 = make_float2(l1x, l1x);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                float v00[CP], v01[CP], v10[CP], v11[CP];
+                load_tap<C>(t00 + m * CP, v00);
+                load_tap<C>(t01 + m * CP, v01);
+                load_tap<C>(t00 + ncols_max * TS + m * CP, v10);
+                load_tap<C>(t01 + ncols_max * TS + m * CP, v11);
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    const bool pad = 2 * j + 1 >= C;   // odd class count: the last pair's second slot is padding
+                    const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
+                    const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
+                    const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
+                    const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
+                    float2 ta = UEM_FFMA2(l1, p01, UEM_FMUL2(l0, p00));
+                    const float2 tb = UEM_FFMA2(l1, p11, UEM_FMUL2(l0, p10));
+                    float2 td = UEM_FADD2(tb, make_float2(-ta.x, -ta.y));
+                    if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
+                    A[m][j] = ta;
+                    D[m][j] = td;
+                }
+            }
+        }
+        cp_async_wait_group<NS - 1>();   // this lane's chunks of row `it` have landed ...
+        __syncwarp();                    // ... and so have the other lanes' (the row is read across lanes)
+        if (active) {
+            const uint32_t rd = rd_base + (uint32_t)stage * kWarpStage;   // this lane's float of plane 0
+            int64_t rid;
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(rid) : "r"(rd + (uint32_t)lane * 4u + (uint32_t)C * 128u));
+            // superpixel view first (its gather is the only long-latency access of the row): multiplicative outside the
+            // ignored id; the ignored id and any id outside [0,R) are redirected to the all-ones sentinel row R
+            const uint32_t lo = (uint32_t)rid, hi = (uint32_t)((uint64_t)rid >> 32);
+            const bool in_region = (hi == 0u) & (lo < Ru) & (lo != ign_lo);
+            const uint32_t r = in_region ? lo : Ru;
+            const float4* wp = swb + r * (uint32_t)(CP / 4);
+            float4 swv[CP / 4];
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) swv[q] = __ldg(wp + q);
+
+            const float2 t2 = make_float2(ly.l1, ly.l1);
+            float2 wgt2[PC];
+            {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
+                float2 z[PC];
+#pragma unroll
+                for (int j = 0; j < PC; ++j) z[j] = UEM_FFMA2(t2, D[0][j], A[0][j]);
+                const float S = exp2_shifted2<PC>(z);
+                const float rs = fmaf(-1e-7f, S, 1.0f);
+                const float2 rs2 = make_float2(rs, rs);
+#pragma unroll
+                for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FMUL2(z[j], rs2);
+            }
+            {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7); the 0.5 of the mean is
+                // folded into the epsilon (q/(max q + 2e-7) == (q/2)/(max q/2 + 1e-7), exact power-of-two scaling)
+                float2 z[PC], z2[PC];
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    z[j] = UEM_FFMA2(t2, D[1][j], A[1][j]);
+                    z2[j] = UEM_FFMA2(t2, D[2][j], A[2][j]);
+                }
+                const float S1 = exp2_shifted2<PC>(z);
+                const float S2 = exp2_shifted2<PC>(z2);
+                // q_c = e1_c/S1 + e2_c/S2, scaled through by S1*S2 (in [1, C^2]): no reciprocal of the two sums
+                const float2 h1v = make_float2(S2, S2), h2v = make_float2(S1, S1);
+                float mx = 0.f;
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    z[j] = UEM_FFMA2(z[j], h1v, UEM_FMUL2(z2[j], h2v));
+                    mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
+                }
+                const float inv = rcp_approx(fmaf(2e-7f, S1 * S2, mx));
+                const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+                for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FFMA2(z[j], inv2, wgt2[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) {
+                wgt2[2 * q] = UEM_FMUL2(wgt2[2 * q], make_float2(swv[q].x, swv[q].y));
+                if (2 * q + 1 < PC) wgt2[2 * q + 1] = UEM_FMUL2(wgt2[2 * q + 1], make_float2(swv[q].z, swv[q].w));
+            }
+            // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
+            float o[C];
+            float s;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                float sv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(rd + (uint32_t)ci * 128u));
+                o[ci] = ((ci & 1) ? wgt2[ci >> 1].y : wgt2[ci >> 1].x) * sv;
+                s = ci ? s + o[ci] : o[ci];
+            }
+            const float inv = rcp_approx(s + 1e-7f);
+            nanacc = fmaf(s, 0.f, nanacc);   // s*0 accumulates to NaN iff a row sum was inf/NaN
+            const uint32_t idx = (uint32_t)y * (uint32_t)W + x;   // < 2^31: one plane of one image
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const float v = o[ci] * inv;
+                cmax[ci] = fmaxf(cmax[ci], v);
+                cmin = fminf(cmin, v);
+                const_cast<float*>(ob + (int64_t)ci * HW)[idx] = v;
+            }
+        }
+        if (++y == H) { y = 0; ++bs; }
+        pstage = stage;
+        if (++stage == NS) stage = 0;
+    }
+    if (p.stats) flush(cur_b);
+}
+
 // superpixel-view weight of every (image, region): softmax(region_max/temp) / (max + 1e-7)  (alignment.py:252-253)
 // table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R+1,CP); row R (the sentinel the ignored
 // id and out-of-range ids are redirected to) is all ones.  On the fused chain the region-max kernel does this itself.
@@ -856,6 +1140,51 @@ static int launch_refine_tma(RefineParams p, cudaStream_t st, bool pdl, bool* do
     return rc;
 }
 
+// column-walk kernel: strips of 128 columns, 4 rows in flight per CTA
+#ifndef UEM_REFINE_COL
+#define UEM_REFINE_COL 1
+#endif
+#ifndef UEM_REFINE_COL_NS
+#define UEM_REFINE_COL_NS 4
+#endif
+#ifndef UEM_REFINE_COL_NT
+#define UEM_REFINE_COL_NT 128
+#endif
+template <int C>
+static int launch_refine_col(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
+    constexpr int NT = UEM_REFINE_COL_NT, NS = UEM_REFINE_COL_NS;
+    *done = false;
+    constexpr float kL2E = 1.4426950408889634f;
+    p.map_scale[0] = kL2E;
+    p.map_scale[1] = p.map_scale[2] = (float)(1.4426950408889634 / (double)p.temp);
+    // low-res columns one warp's 32 image columns can span (+1 for the right neighbour)
+    int ncols_max = (int)(31.0f * p.sx) + 3;
+    if (ncols_max > p.w) ncols_max = p.w;
+    const size_t smem = (size_t)NS * NT * (4 * C + 8) + (size_t)(NT / 32) * 2 * ncols_max * 3 * cp_of(C) * 4;
+    if (smem > 100 * 1024 || (int64_t)p.H * p.W >= ((int64_t)1 << 31)) return 0;   // generic kernels take it
+    auto kernel = refine_col_kernel<C, NT, NS>;
+    if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int nstrips = (p.W + NT - 1) / NT;
+    const int64_t total = (int64_t)p.b * nstrips * p.H;
+    const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    UEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, ncols_max));
+    *done = true;
+    return 0;
+}
+
 // sw_ws: b*(R+1)*CP floats of scratch for the per-region weights (superpixel view only)
 static int launch_refine(int views, const float* simi, const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                          const void* table, int table_encoded, int64_t R, const int64_t* ignored_id, const float* soft, int b,
@@ -895,6 +1224,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     const bool vec = (W % 4 == 0) && uem_aligned16(soft) && uem_aligned16(out) && (!sup || uem_aligned16(sup));
     const bool fast = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2 && 3.0f * p.sx <= 0.999f &&
                       (w % 4 == 0) && uem_aligned16(simi) && uem_aligned16(pred1) && uem_aligned16(pred2);
+    // column-walk kernel: any up-sampling ratio, any low-res width
+    const bool colwalk = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2;
     void *ev0 = nullptr, *ev1 = nullptr;
     int launched = 1, rc = 0;
     UEM_DISPATCH_C(c, {
@@ -907,7 +1238,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
         bool done = false;
-        if (fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0, &done);
+        if (UEM_REFINE_COL && colwalk) rc = launch_refine_col<C>(p, st, pdl && weights_ready && !ev0, &done);
+        if (!done && rc == 0 && fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0, &done);
         if (!done && rc == 0) {
             const int vecw = vec ? 4 : 1;
             const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
