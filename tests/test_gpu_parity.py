@@ -311,6 +311,65 @@ def test_ragged_shapes_scalar_path(dev, shape):
     _eq(ops.hist_f32(x.to(dev), 30, 0.0, 1.0), torch.histc(x, 30, 0.0, 1.0).long(), "histc")
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 72, 200, 9, 25), (1, 7, 40, 36, 20, 18), (3, 2, 33, 64, 3, 5), (1, 8, 64, 256, 4, 16),
+                                   (2, 6, 50, 132, 50, 132), (1, 3, 1, 8, 1, 2)])
+@pytest.mark.parametrize("temp", [2.0, 1.7])
+def test_refine_column_kernel_shapes(dev, shape, temp):
+    """Default configuration (all views, two heads, W % 4 == 0) at shapes that stress the column-walk kernel: partial
+    and empty warps of the last 128-column strip, odd class counts, up-sampling ratios from 1 to 16, one-row maps."""
+    from oracle import uem_oracle as O
+    from uemda_b200 import mining
+    b, c, H, W, h, w = shape
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    soft = torch.softmax(torch.randn(b, c, H, W, generator=g) * 3, dim=1)
+    sup = torch.randint(0, 11, (b, 1, H, W), generator=g)
+    k = 19
+    feat = torch.randn(b, k, h, w, generator=g)
+    protos = torch.randn(c, k, generator=g)
+    p1 = torch.randn(b, c, h, w, generator=g) * 4
+    p2 = torch.randn(b, c, h, w, generator=g) * 4
+    want = O.label_refine(sup, feat, [p1, p2], soft, protos, mode="all", temp=temp)
+    got, _ = mining.refine_select(7, soft.to(dev), temp, feat=feat.to(dev), prototypes=protos.to(dev), pred1=p1.to(dev),
+                                  pred2=p2.to(dev), sup=sup.to(dev))
+    assert_close(got, want, rtol=RTOL, atol=1e-7, what="refine column kernel %s temp=%s" % (shape, temp))
+    # per-(image, class) maxima that feed pseudo_selection come out of the same pass
+    stats = got._uem_stats[0]
+    hard = O.pseudo_select(got.cpu())
+    from uemda_b200 import ops
+    _eq(ops.pseudo_select_stats(got, stats, 0.8, 0.6, -1), hard, "selection from the kernel's own class statistics")
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 72, 200, 9, 25), (1, 7, 41, 37, 20, 18), (3, 2, 33, 64, 3, 5), (1, 8, 64, 256, 4, 16),
+                                   (2, 6, 50, 131, 50, 131), (1, 3, 1, 8, 1, 2), (1, 1, 9, 9, 3, 3)])
+@pytest.mark.parametrize("heads,temp", [(2, 1.0), (1, 1.0), (2, 1.7)])
+def test_logits_pass_shapes(dev, shape, heads, temp):
+    """a1-a4 at ragged shapes: odd widths, partial strips, one or two heads, temperature, up-sampling ratios 1..16."""
+    from oracle import uem_oracle as O
+    from uemda_b200 import ops
+    b, c, H, W, h, w = shape
+    g = torch.Generator().manual_seed(H * 977 + W)
+    x1 = torch.randn(b, c, h, w, generator=g) * 4
+    x2 = torch.randn(b, c, h, w, generator=g) * 4 if heads == 2 else None
+    want = O.soft_from_logits(x1 / temp, None if x2 is None else x2 / temp, (H, W))
+    out = ops.softmax_conf_entropy_argmax(x1.to(dev), None if x2 is None else x2.to(dev), size=(H, W), temp=temp)
+    assert_close(out["soft"], want, rtol=RTOL, atol=1e-8, what="soft from logits %s" % (shape,))
+    conf, arg = O.confidence_argmax(want)
+    assert_close(out["conf"], conf, rtol=RTOL, atol=1e-8, what="conf")
+    # entropy of the kernel's own probabilities: 1e-5.  Against the entropy of the reference's probabilities the term of a
+    # dominant class (-p log p ~ 1 - p) moves by an ulp of p ~ 1, i.e. ~1e-7 absolute whatever the size of the entropy:
+    # absolute tolerance 1e-6 there.
+    assert_close(out["entropy"].reshape(-1), O.entropy(out["soft"].cpu()), rtol=RTOL, atol=1e-7, what="entropy of own soft")
+    assert_close(out["entropy"].reshape(-1), O.entropy(want), rtol=RTOL, atol=1e-6, what="entropy from logits")
+    if c > 1:
+        top2 = want.topk(2, dim=1)[0]
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-5
+        assert bool((out["argmax"].cpu()[clear] == arg[clear]).all())
+    # argmax is exactly the first maximum of the kernel's own soft output (documented tie-break)
+    _eq(out["argmax"], out["soft"].cpu().max(dim=1)[1], "argmax of own soft")
+    only = ops.softmax_conf_entropy_argmax(x1.to(dev), None if x2 is None else x2.to(dev), size=(H, W), temp=temp, want=("argmax",))
+    _eq(only["argmax"], out["argmax"], "argmax-only call")
+
+
 def test_full_size_properties(dev):
     """BASELINE config 2 at full size (8x6x512x512, k=2048): size-independent properties instead of the
     (slow) oracle -- refined rows sum to ~1, hard labels equal the argmax wherever kept, thresholds

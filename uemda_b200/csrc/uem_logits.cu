@@ -98,6 +98,187 @@ __global__ void __launch_bounds__(256) logits_pass_kernel(const float* __restric
     (void)inv_temp;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column-walk form of the fused logits pass (same decomposition as refine_col_kernel, uem_refine.cu): a thread owns
+// ONE image column of a 128-column strip and walks down a contiguous range of rows.  The horizontal half of the
+// bilinear interpolation is done once per low-res row pair (A = lerp_x(row i0), B = lerp_x(row i1), kept in registers
+// pre-scaled by log2 e / temp as A and D = B - A); per output row a logit is one packed FFMA (z = A + t_y * D) and the
+// softmax exponent a bare EX2.  There is no full-resolution input at all: the kernel is bound by its stores
+// (4c + 16 bytes per pixel), which are 32-bit per lane and contiguous over the warp (full 128-byte lines).
+// ------------------------------------------------------------------------------------------------
+template <int C, int NM>
+__global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int b, int h,
+                                                            int w, int H, int W, float sy, float sx, float scale,
+                                                            float* __restrict__ soft, float* __restrict__ conf,
+                                                            float* __restrict__ entropy, int64_t* __restrict__ argmax,
+                                                            const int ncols_max) {
+    constexpr int NT = 128, CP = (C + 3) & ~3, PC = (C + 1) / 2, TS = NM * CP;
+    extern __shared__ __align__(16) float taps_all[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float* const taps = taps_all + (size_t)wid * 2 * ncols_max * TS;
+    const int64_t HW = (int64_t)H * W;
+    const int hw_low = h * w;
+    const int nstrips = (W + NT - 1) / NT;
+    const int64_t total = (int64_t)b * nstrips * H;
+    const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int n = (int)(U1 - U0);
+    if (n <= 0) return;
+    int bs = (int)(U0 / H), y = (int)(U0 - (int64_t)bs * H);
+    const float* maps[2] = {x1, x2};
+
+    float2 A[NM][PC], D[NM][PC];
+    int cur_bs = -1, cur_i0 = -1, bi = 0;
+    int a0 = 0, a1 = 0, abase = 0, ncols = 1;
+    float l0x = 0.f, l1x = 0.f;
+    bool active = false;
+    uint32_t x = 0;
+    for (int it = 0; it < n; ++it) {
+        if (bs != cur_bs) {        // new (image, strip): column geometry
+            bi = bs / nstrips;
+            const int xw = (bs - bi * nstrips) * NT + wid * 32;
+            x = (uint32_t)(xw + lane);
+            active = (int)x < W;
+            const Lerp lx = make_lerp(active ? (int)x : W - 1, w, sx);
+            a0 = lx.i0; a1 = lx.i1; l0x = lx.l0; l1x = lx.l1;
+            abase = make_lerp(min(xw, W - 1), w, sx).i0;
+            ncols = make_lerp(min(xw + 31, W - 1), w, sx).i1 - abase + 1;
+            cur_bs = bs;
+            cur_i0 = -1;
+        }
+        const Lerp ly = make_lerp(y, h, sy);
+        if (ly.i0 != cur_i0) {     // new low-res row pair: fetched once per warp, interpolated horizontally once per lane
+            cur_i0 = ly.i0;
+            __syncwarp();
+            if (lane < NM * C) {
+                const int m = lane / C, ci = lane - m * C;
+                const float* plane = maps[m] + ((int64_t)bi * C + ci) * hw_low + abase;
+                float* dst = taps + m * CP + ci;
+                const float* r0 = plane + ly.i0 * w;
+                const float* r1 = plane + ly.i1 * w;
+                for (int j = 0; j < ncols; ++j) {
+                    dst[j * TS] = __ldg(r0 + j) * scale;
+                    dst[(ncols_max + j) * TS] = __ldg(r1 + j) * scale;
+                }
+            }
+            __syncwarp();
+            const float* t00 = taps + (a0 - abase) * TS;
+            const float* t01 = taps + (a1 - abase) * TS;
+            const float2 l0 = make_float2(l0x, l0x), l1 = make_float2(l1x, l1x);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                float v00[CP], v01[CP], v10[CP], v11[CP];
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 q00 = *reinterpret_cast<const float4*>(t00 + m * CP + 4 * q);
+                    const float4 q01 = *reinterpret_cast<const float4*>(t01 + m * CP + 4 * q);
+                    const float4 q10 = *reinterpret_cast<const float4*>(t00 + ncols_max * TS + m * CP + 4 * q);
+                    const float4 q11 = *reinterpret_cast<const float4*>(t01 + ncols_max * TS + m * CP + 4 * q);
+                    v00[4 * q] = q00.x; v00[4 * q + 1] = q00.y; v00[4 * q + 2] = q00.z; v00[4 * q + 3] = q00.w;
+                    v01[4 * q] = q01.x; v01[4 * q + 1] = q01.y; v01[4 * q + 2] = q01.z; v01[4 * q + 3] = q01.w;
+                    v10[4 * q] = q10.x; v10[4 * q + 1] = q10.y; v10[4 * q + 2] = q10.z; v10[4 * q + 3] = q10.w;
+                    v11[4 * q] = q11.x; v11[4 * q + 1] = q11.y; v11[4 * q + 2] = q11.z; v11[4 * q + 3] = q11.w;
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    const bool pad = 2 * j + 1 >= C;
+                    const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
+                    const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
+                    const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
+                    const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
+                    float2 ta = __ffma2_rn(l1, p01, __fmul2_rn(l0, p00));
+                    const float2 tb = __ffma2_rn(l1, p11, __fmul2_rn(l0, p10));
+                    float2 td = __fadd2_rn(tb, make_float2(-ta.x, -ta.y));
+                    if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
+                    A[m][j] = ta;
+                    D[m][j] = td;
+                }
+            }
+        }
+        if (active) {
+            const float2 t2 = make_float2(ly.l1, ly.l1);
+            float pr[C];
+            {
+                float2 e[NM][PC];
+                float rs[NM];
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        e[m][j] = __ffma2_rn(t2, D[m][j], A[m][j]);
+                        mx = fmaxf(mx, fmaxf(e[m][j].x, e[m][j].y));
+                    }
+                    float2 acc;
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        const float2 d = __fadd2_rn(e[m][j], make_float2(-mx, -mx));
+                        e[m][j] = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                        acc = j ? __fadd2_rn(acc, e[m][j]) : e[m][j];
+                    }
+                    // 1/S, Newton-refined (rcp.approx alone is 1 ulp; the soft labels are this kernel's product)
+                    const float S = acc.x + acc.y;
+                    float r = rcp_approx(S);
+                    r = fmaf(r, fmaf(-S, r, 1.0f), r);
+                    rs[m] = (NM == 2) ? 0.5f * r : r;
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    float2 q = __fmul2_rn(e[0][j], make_float2(rs[0], rs[0]));
+                    if (NM == 2) q = __ffma2_rn(e[1][j], make_float2(rs[1], rs[1]), q);
+                    pr[2 * j] = q.x;
+                    if (2 * j + 1 < C) pr[2 * j + 1] = q.y;
+                }
+            }
+            float best = -INFINITY;
+            int arg = 0;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {   // first (lowest) index wins ties: torch.max / argmax
+                const bool gt = pr[ci] > best;
+                best = gt ? pr[ci] : best;
+                arg = gt ? ci : arg;
+            }
+            const uint32_t idx = (uint32_t)y * (uint32_t)W + x;
+            if (soft) {
+                float* sb = soft + (int64_t)bi * C * HW;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) (sb + (int64_t)ci * HW)[idx] = pr[ci];
+            }
+            if (conf) (conf + (int64_t)bi * HW)[idx] = best;
+            if (entropy) (entropy + (int64_t)bi * HW)[idx] = entropy_px<C>(pr);   // balance.py:372; p==0 -> NaN like the reference
+            if (argmax) (argmax + (int64_t)bi * HW)[idx] = arg;
+        }
+        if (++y == H) { y = 0; ++bs; }
+    }
+}
+
+template <int C, int NM>
+static int launch_logits_col(const float* x1, const float* x2, int b, int h, int w, int H, int W, float sy, float sx, float temp,
+                             float* soft, float* conf, float* entropy, int64_t* argmax, cudaStream_t st, bool* done) {
+    *done = false;
+    constexpr int CP = (C + 3) & ~3;
+    int ncols_max = (int)(31.0f * sx) + 3;
+    if (ncols_max > w) ncols_max = w;
+    const size_t smem = (size_t)4 * 2 * ncols_max * NM * CP * 4;
+    if (smem > 64 * 1024 || (int64_t)H * W >= ((int64_t)1 << 31)) return 0;
+    auto kernel = logits_col_kernel<C, NM>;
+    if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = UEM_SMS;
+    }
+    const int64_t total = (int64_t)b * ((W + 127) / 128) * H;
+    const int grid = (int)min(total, (int64_t)sms * per_sm);
+    kernel<<<grid, 128, smem, st>>>(x1, x2, b, h, w, H, W, sy, sx, (float)(1.4426950408889634 / (double)temp), soft, conf, entropy,
+                                    argmax, ncols_max);
+    *done = true;
+    return 0;
+}
+
 // entropy (+ optional UVEM weight / gate / valid count) of a probability map (b,c,HW)
 template <int C, int VEC, bool TERMS>
 __global__ void __launch_bounds__(256) entropy_weight_kernel(const float* __restrict__ soft, const int64_t* __restrict__ target,
@@ -171,6 +352,19 @@ extern "C" int uem_softmax_conf_entropy_argmax_f32(const float* x1, const float*
                      (!entropy || uem_aligned16(entropy)) && (!argmax || uem_aligned16(argmax));
     const float sy = uem_align_corners_scale(h, H), sx = uem_align_corners_scale(w, W);
     const int nmaps = x2 ? 2 : 1;
+    {   // column-walk kernel (any width: its stores are scalar per lane)
+        bool done = false;
+        int rc = 0;
+        UEM_DISPATCH_C(c, {
+            if (nmaps == 2) rc = launch_logits_col<C, 2>(x1, x2, b, h, w, H, W, sy, sx, temp, soft, conf, entropy, argmax, st, &done);
+            else rc = launch_logits_col<C, 1>(x1, x2, b, h, w, H, W, sy, sx, temp, soft, conf, entropy, argmax, st, &done);
+        });
+        if (rc) return rc;
+        if (done) {
+            UEM_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     UEM_DISPATCH_C(c, {
         size_t smem = (size_t)nmaps * C * w * sizeof(float);
         UEM_REQUIRE(smem <= 227 * 1024, "uem_softmax_conf_entropy_argmax_f32: low-res width %d too large", w);
