@@ -469,7 +469,7 @@ def main():
     if rank == 0:
         peak, peak_src = peak_hbm()
         alg_bytes = wl.pixels * (4 * wl.c + 8 + 4 * wl.c)  # refine kernel: read soft + sup, write refined
-        roof = {"bound": "hbm", "kernel": "refine_kernel (fused label_refine, all views)", "achieved": None, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "refine_col_kernel (fused label_refine, all views)", "achieved": None, "peak": peak,
                 "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
                 "kernel_ms": refine_ms}
         if refine_ms:

@@ -726,6 +726,13 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_k
 //   * the global stores are 32-bit per lane, contiguous over the warp (full 128-byte lines), class maps stay planar.
 // 1 pixel per thread keeps the state at 6*PC registers + temporaries, so 5 CTAs of 128 threads are resident per SM.
 // ------------------------------------------------------------------------------------------------
+// region-weight gather: keep the table rows in L1 (neighbouring pixels and rows hit the same 32 bytes)
+__device__ __forceinline__ float4 ldg_f4_l1(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
 #ifndef UEM_REFINE_COL_MINB
 #define UEM_REFINE_COL_MINB 4   // 128 registers: no spills for C <= 8 (5 resident CTAs spill and run 30% slower at C = 7)
 #endif
@@ -924,7 +931,7 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
             const float4* wp = swb + r * (uint32_t)(CP / 4);
             float4 swv[CP / 4];
 #pragma unroll
-            for (int q = 0; q < CP / 4; ++q) swv[q] = __ldg(wp + q);
+            for (int q = 0; q < CP / 4; ++q) swv[q] = ldg_f4_l1(wp + q);
 
             const float2 t2 = make_float2(ly.l1, ly.l1);
             float2 wgt2[PC];
@@ -968,14 +975,20 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
             }
             // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
             float o[C];
-            float s;
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
                 float sv;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(rd + (uint32_t)ci * 128u));
                 o[ci] = ((ci & 1) ? wgt2[ci >> 1].y : wgt2[ci >> 1].x) * sv;
-                s = ci ? s + o[ci] : o[ci];
             }
+            float ps[PC];   // pairwise tree: depth log2(C) instead of a chain of C dependent adds
+#pragma unroll
+            for (int j = 0; j < PC; ++j) ps[j] = (2 * j + 1 < C) ? o[2 * j] + o[2 * j + 1] : o[2 * j];
+#pragma unroll
+            for (int st2 = 1; st2 < PC; st2 *= 2)
+#pragma unroll
+                for (int j = 0; j + st2 < PC; j += 2 * st2) ps[j] += ps[j + st2];
+            const float s = ps[0];
             const float inv = rcp_approx(s + 1e-7f);
             nanacc = fmaf(s, 0.f, nanacc);   // s*0 accumulates to NaN iff a row sum was inf/NaN
             const uint32_t idx = (uint32_t)y * (uint32_t)W + x;   // < 2^31: one plane of one image
