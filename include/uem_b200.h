@@ -243,6 +243,21 @@ UEM_API int uem_pcl_forward_f32(const float* feat, int b, int k, int64_t hw, con
 UEM_API int uem_pcl_backward_f32(const float* feat, int b, int k, int64_t hw, int c, const float* coef,
                          const float* grad_out, float* grad_feat, const void* ws, void* stream);
 
+/* ---- UVEM / UPS target loss fused end to end, forward + backward (next row) ----------
+ * uemda/gast/balance.py:437-457 (loss_calc_uvem: every head's logits up-sampled bilinearly, align_corners=True, to the
+ * label size; loss averaged over heads), :356-394 (UVEMLoss.forward), :321-342 (UPSLoss.forward).
+ * x1 [, x2] (b,c,h,w) low-resolution logits of the heads (x2 may be NULL), target (b,H,W) int64, coef (b*H*W) fp32: the
+ * detached per-pixel factor weight x gate x class weight (0 for ignored / gated pixels; from uem_uvem_terms_f32).
+ * forward : sums[m] += sum_px coef * CrossEntropy(upsample(x_m))[px, target]   (fp64, zeroed by the caller); the loss
+ *           is (sums[0] [+ sums[1]]) / (valid + 1e-7) / heads.
+ * backward: g_m (b,c,h,w) = scale[0] * d sums[m] / d x_m, every element written, deterministic (a gather per low-res
+ *           cell, no atomics); scale: device scalar = grad_out / (valid + 1e-7) / heads. */
+UEM_API int uem_uvem_loss_forward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
+                              const int64_t* target, const float* coef, double* sums, void* stream);
+UEM_API int uem_uvem_loss_backward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
+                               const int64_t* target, const float* coef, const float* scale, float* g1, float* g2,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

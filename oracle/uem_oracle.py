@@ -389,3 +389,33 @@ def pcl_loss(protos, feat, labels, temperature=8.0, ignore_label=-1):
     protos = F.normalize(protos, p=2, dim=1)
     logits = feat.mm(protos.permute(1, 0).contiguous()) / temperature   # :43-44
     return F.cross_entropy(logits, labels)                   # :46
+
+
+# --------------------------------------------------------------------------------------
+# f3: UVEM / UPS target loss over up-sampled heads
+# --------------------------------------------------------------------------------------
+def uvem_loss_calc(heads, label, label_soft, m=0.1, threshold=0.7, gamma=8.0, use_weight=True, balance_freq=None,
+                   class_num=None, ignore_label=-1, multi=True):
+    """loss_calc_uvem (balance.py:437-457) over UVEMLoss.forward (:356-394) or, with use_weight=False,
+    UPSLoss.forward (:321-342).  heads: list of (b,c,h,w) logits (autograd flows into them); balance_freq: None or the
+    ClassBalance frequency vector, which moves once PER HEAD exactly as in the reference (the loss is called per head).
+    Returns (loss, final balance_freq)."""
+    heads = list(heads) if multi else [heads]
+    c = label_soft.shape[1]
+    class_num = class_num or c
+    t_ = label.long().reshape(-1)
+    u = entropy(label_soft).detach()
+    total = 0
+    for p in heads:
+        if p.shape[-2:] != label.shape[-2:]:
+            p = upsample_bilinear(p, label.shape[-2:])
+        p_ = p.permute(0, 2, 3, 1).reshape(-1, c)
+        ce = F.cross_entropy(p_, t_, reduction="none", ignore_index=ignore_label)
+        ce = torch.where(u > threshold, torch.zeros_like(ce), ce)
+        weight = uvem_weight(u, m, threshold, gamma) if use_weight else 1.0
+        if balance_freq is not None:
+            balance_freq, _, cw = class_balance_step(balance_freq, t_, class_num, ignore_label)
+            weight = weight * cw
+        valid = torch.sum((u <= threshold) & (t_ != ignore_label))
+        total = total + (weight * ce).sum() / (valid + 1e-7)
+    return (total / len(heads) if multi else total), balance_freq

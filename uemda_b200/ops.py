@@ -440,3 +440,39 @@ def pcl_backward(feat, coef, ws, grad_out=None):
     g = None if grad_out is None else L.f32c(grad_out.detach()).reshape(1)
     L.check(lib.uem_pcl_backward_f32(L.ptr(feat), b, k, h * w, c, L.ptr(coef), L.ptr(g), L.ptr(grad), L.ptr(ws), L.stream_of(feat)))
     return grad
+
+
+# --------------------------------------------------------------------------------------------- f3
+def uvem_loss_forward(x1, x2, target, coef):
+    """sum_px coef * CE(upsample(x_m))[target] per head -> (heads,) float64 (balance.py:356-394, :437-457)."""
+    L.require_cuda(x1, x2, target, coef)
+    x1 = L.f32c(x1.detach())
+    x2 = None if x2 is None else L.f32c(x2.detach())
+    target = L.i64c(target.detach())
+    coef = L.f32c(coef.detach()).reshape(-1)
+    b, c, h, w = x1.shape
+    H, W = target.shape[-2:]
+    assert target.numel() == b * H * W and coef.numel() == b * H * W and (x2 is None or x2.shape == x1.shape)
+    lib = L.bind(x1)
+    sums = torch.zeros(2 if x2 is not None else 1, dtype=torch.float64, device=x1.device)
+    L.check(lib.uem_uvem_loss_forward_f32(L.ptr(x1), L.ptr(x2), b, c, h, w, H, W, L.ptr(target), L.ptr(coef), L.ptr(sums),
+                                          L.stream_of(x1)))
+    return sums
+
+
+def uvem_loss_backward(x1, x2, target, coef, scale):
+    """scale * d/dx_m sum_px coef * CE(upsample(x_m))[target]; deterministic gather per low-res cell."""
+    L.require_cuda(x1, x2, target, coef, scale)
+    x1 = L.f32c(x1.detach())
+    x2 = None if x2 is None else L.f32c(x2.detach())
+    target = L.i64c(target.detach())
+    coef = L.f32c(coef.detach()).reshape(-1)
+    scale = L.f32c(scale.detach()).reshape(1)
+    b, c, h, w = x1.shape
+    H, W = target.shape[-2:]
+    lib = L.bind(x1)
+    g1 = torch.empty_like(x1)
+    g2 = None if x2 is None else torch.empty_like(x2)
+    L.check(lib.uem_uvem_loss_backward_f32(L.ptr(x1), L.ptr(x2), b, c, h, w, H, W, L.ptr(target), L.ptr(coef), L.ptr(scale),
+                                           L.ptr(g1), L.ptr(g2), L.stream_of(x1)))
+    return g1, g2
