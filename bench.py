@@ -279,7 +279,7 @@ def main():
         sums, counts = source_stats(s)
         mx = ops.i64_minmax(s["sup"])[1:]
         cur.wait_stream(side)
-        packed_bufs[j].copy_(mining.pack_local(sums, counts, mx))
+        ops.pack_local(sums, counts, mx, out=packed_bufs[j])
 
     def phase_b(s, j):
         sums, counts, ignored = miner.fold(gathered_bufs[j])

@@ -243,6 +243,15 @@ UEM_API int uem_pcl_forward_f32(const float* feat, int b, int k, int64_t hw, con
 UEM_API int uem_pcl_backward_f32(const float* feat, int b, int k, int64_t hw, int c, const float* coef,
                          const float* grad_out, float* grad_feat, const void* ws, void* stream);
 
+/* ---- multi-GPU exchange helpers -----------------------------------------------------
+ * The rank-local statistics of a step travel as one fp64 vector [c*k prototype sums | c counts | max superpixel id]
+ * (every part exact in fp64); uem_fold_gathered_f64 folds the all-gathered (world, c*k+c+1) matrix in rank order, so
+ * every rank gets bit-identical sums (alignment.py:347-353) and the batch-global max id (alignment.py:241). */
+UEM_API int uem_pack_local_f64(const float* sums, const int64_t* counts, const int64_t* max_id, int c, int k, double* out,
+                       void* stream);
+UEM_API int uem_fold_gathered_f64(const double* gathered, int world, int c, int k, float* sums, int64_t* counts,
+                          int64_t* max_id, void* stream);
+
 /* ---- UVEM / UPS target loss fused end to end, forward + backward (next row) ----------
  * uemda/gast/balance.py:437-457 (loss_calc_uvem: every head's logits up-sampled bilinearly, align_corners=True, to the
  * label size; loss averaged over heads), :356-394 (UVEMLoss.forward), :321-342 (UPSLoss.forward).

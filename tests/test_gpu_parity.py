@@ -679,3 +679,25 @@ def test_uvem_loss_vs_oracle_shapes(dev, shape):
     up = [tnf.interpolate(x, size=(H, W), mode="bilinear", align_corners=True) for x in ux]
     unfused = (fn(up[0], label.to(dev), soft.to(dev)) + fn(up[1], label.to(dev), soft.to(dev))) / 2
     assert_close(unfused.detach().reshape(()), loss.detach().reshape(()), rtol=RTOL, atol=0, what="fused vs unfused loss")
+
+
+def test_exchange_pack_and_fold_kernels(dev):
+    """8e: the one-launch pack / rank-ordered fold of the exchange vector equal the elementwise torch form bit for bit."""
+    from uemda_b200 import mining, ops
+    g = torch.Generator().manual_seed(5)
+    c, k, world = 6, 2048, 3
+    rows = []
+    for r in range(world):
+        sums = torch.randn(c, k, generator=g) * 1000
+        counts = torch.randint(0, 1 << 40, (c,), generator=g)
+        mx = torch.randint(0, 1 << 33, (1,), generator=g)
+        want = mining.pack_local(sums, counts, mx)                       # CPU tensors: elementwise torch form
+        got = ops.pack_local(sums.to(dev), counts.to(dev), mx.to(dev))
+        _eq(got, want, "pack rank %d" % r)
+        rows.append(want)
+    gathered = torch.stack(rows)
+    ws, wc, wm = mining.fold_gathered(gathered, c, k)                    # CPU form
+    gs, gc, gm = ops.fold_gathered(gathered.to(dev), c, k)
+    _eq(gs, ws, "folded sums")
+    _eq(gc, wc, "folded counts")
+    _eq(gm, wm, "folded max id")

@@ -67,6 +67,8 @@ SIGNATURES = {
     "uem_pcl_ws_bytes": (_L, [_I, _I, _L]),
     "uem_pcl_forward_f32": (_I, [_P, _I, _I, _L, _P, _I, _P, _L, _F, _P, _P, _P, _P]),
     "uem_pcl_backward_f32": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P]),
+    "uem_pack_local_f64": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "uem_fold_gathered_f64": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "uem_uvem_loss_forward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "uem_uvem_loss_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }

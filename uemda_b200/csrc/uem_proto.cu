@@ -686,3 +686,55 @@ extern "C" int uem_proto_finalize_ema_f32(const float* sums, const int64_t* coun
     UEM_CHECK_LAUNCH();
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU exchange helpers: the rank-local statistics of a step travel as ONE fp64 vector
+// [c*k prototype sums | c counts | max superpixel id]; every part is exact in fp64.  One launch packs it, one launch
+// folds the all-gathered (world, n) matrix in RANK ORDER (so every rank gets bit-identical sums) back into fp32 sums,
+// int64 counts and the batch-global max id (alignment.py:241, :347-353).  They replace ~13 tiny elementwise launches
+// that sat on the critical path of every sharded step.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) pack_local_kernel(const float* __restrict__ sums, const int64_t* __restrict__ counts,
+                                                         const int64_t* __restrict__ max_id, int ck, int c, double* __restrict__ out) {
+    const int n = ck + c + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = i < ck ? (double)sums[i] : (i < ck + c ? (double)counts[i - ck] : (double)max_id[0]);
+}
+__global__ void __launch_bounds__(256) fold_gathered_kernel(const double* __restrict__ gathered, int world, int ck, int c,
+                                                            float* __restrict__ sums, int64_t* __restrict__ counts,
+                                                            int64_t* __restrict__ max_id) {
+    const int n = ck + c + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double tot = gathered[i];
+        if (i < ck + c) {
+            for (int r = 1; r < world; ++r) tot += gathered[(int64_t)r * n + i];   // rank order: identical on every rank
+            if (i < ck) sums[i] = (float)tot;
+            else counts[i - ck] = llrint(tot);
+        } else {
+            for (int r = 1; r < world; ++r) tot = fmax(tot, gathered[(int64_t)r * n + i]);
+            max_id[0] = llrint(tot);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int uem_pack_local_f64(const float* sums, const int64_t* counts, const int64_t* max_id, int c, int k, double* out,
+                                  void* stream) {
+    UEM_REQUIRE(sums && counts && max_id && out && c > 0 && k > 0, "uem_pack_local_f64: bad arguments");
+    const int n = c * k + c + 1;
+    pack_local_kernel<<<min(uem_div_up(n, 256), UEM_SMS), 256, 0, (cudaStream_t)stream>>>(sums, counts, max_id, c * k, c, out);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_fold_gathered_f64(const double* gathered, int world, int c, int k, float* sums, int64_t* counts,
+                                     int64_t* max_id, void* stream) {
+    UEM_REQUIRE(gathered && sums && counts && max_id && world > 0 && c > 0 && k > 0, "uem_fold_gathered_f64: bad arguments");
+    const int n = c * k + c + 1;
+    fold_gathered_kernel<<<min(uem_div_up(n, 256), UEM_SMS), 256, 0, (cudaStream_t)stream>>>(gathered, world, c * k, c, sums, counts,
+                                                                                            max_id);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}

@@ -129,12 +129,16 @@ def unpack_stats(buf, c, k, with_hist):
 def pack_local(sums, counts, max_id):
     """[c*k sums | c counts | max superpixel id] as one fp64 vector: the rank-local statistics of one step.
     Every part is exact in fp64 (fp32 sums, integer counts and ids < 2^53)."""
+    if sums.is_cuda:
+        return ops.pack_local(sums, counts, max_id)   # one launch
     return torch.cat([sums.reshape(-1).double(), counts.reshape(-1).double(), max_id.reshape(-1)[:1].double()])
 
 
 def fold_gathered(gathered, c, k):
     """(world, c*k+c+1) all-gathered rank vectors -> (sums (c,k) fp32, counts (c,) int64, global max id (1,) int64).
     The sum runs over ranks in rank order on every rank, so all ranks get bit-identical prototypes."""
+    if gathered.is_cuda:
+        return ops.fold_gathered(gathered.contiguous(), c, k)   # one launch
     tot = gathered[0].clone()
     for r in range(1, gathered.shape[0]):
         tot[:c * k + c] += gathered[r, :c * k + c]
@@ -168,10 +172,14 @@ class ShardedMiner:
         al = self.aligner
         down = al.downscale_gt(label_s_local)
         sums, counts = ops.proto_accumulate(feat_s_local, down, al.class_num, al.ignore_label)
-        packed = pack_local(sums, counts, ops.i64_minmax(sup_local)[1:])
-        if out is not None:
-            out.copy_(packed)
-            packed = out
+        mx = ops.i64_minmax(sup_local)[1:]
+        if out is not None and sums.is_cuda:
+            packed = ops.pack_local(sums, counts, mx, out=out)
+        else:
+            packed = pack_local(sums, counts, mx)
+            if out is not None:
+                out.copy_(packed)
+                packed = out
         return packed, down
 
     def exchange(self, packed, out=None):

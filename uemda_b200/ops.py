@@ -476,3 +476,32 @@ def uvem_loss_backward(x1, x2, target, coef, scale):
     L.check(lib.uem_uvem_loss_backward_f32(L.ptr(x1), L.ptr(x2), b, c, h, w, H, W, L.ptr(target), L.ptr(coef), L.ptr(scale),
                                            L.ptr(g1), L.ptr(g2), L.stream_of(x1)))
     return g1, g2
+
+
+# --------------------------------------------------------------------------------------------- 8e
+def pack_local(sums, counts, max_id, out=None):
+    """[c*k sums | c counts | max id] -> (c*k+c+1,) float64 in one launch (the rank-local statistics of a step)."""
+    L.require_cuda(sums, counts, max_id)
+    sums = L.f32c(sums.detach())
+    counts = L.i64c(counts.detach())
+    max_id = L.i64c(max_id.detach()).reshape(-1)
+    c, k = sums.shape
+    lib = L.bind(sums)
+    if out is None:
+        out = torch.empty(c * k + c + 1, dtype=torch.float64, device=sums.device)
+    assert out.dtype == torch.float64 and out.numel() == c * k + c + 1 and out.is_contiguous()
+    L.check(lib.uem_pack_local_f64(L.ptr(sums), L.ptr(counts), L.ptr(max_id), c, k, L.ptr(out), L.stream_of(sums)))
+    return out
+
+
+def fold_gathered(gathered, c, k):
+    """(world, c*k+c+1) float64 -> (sums (c,k) fp32, counts (c,) int64, max id (1,) int64), ranks folded in rank order."""
+    L.require_cuda(gathered)
+    assert gathered.dtype == torch.float64 and gathered.is_contiguous() and gathered.shape[1] == c * k + c + 1
+    lib = L.bind(gathered)
+    sums = torch.empty((c, k), dtype=torch.float32, device=gathered.device)
+    counts = torch.empty((c,), dtype=torch.int64, device=gathered.device)
+    max_id = torch.empty((1,), dtype=torch.int64, device=gathered.device)
+    L.check(lib.uem_fold_gathered_f64(L.ptr(gathered), gathered.shape[0], c, k, L.ptr(sums), L.ptr(counts), L.ptr(max_id),
+                                      L.stream_of(gathered)))
+    return sums, counts, max_id
