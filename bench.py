@@ -256,10 +256,11 @@ def main():
             down = al.downscale_gt(s["label_s"])
             return ops.proto_accumulate(s["feat_s"], down, wl.c, -1, fold=fold)
 
-    def target_chain(s, ignored):
+    def target_chain(s, ignored, ws_=None, regions_ready=False):
         return mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=proto_state, pred1=s["pred1"],
                                     pred2=s["pred2"], sup=s["sup"], num_regions=R, ignored_id=ignored, eps=al.eps,
-                                    select=(CUTOFF[0], CUTOFF[1], -1), ws=ws, uvem=UVEM)
+                                    select=(CUTOFF[0], CUTOFF[1], -1), ws=ws if ws_ is None else ws_, uvem=UVEM,
+                                    regions_ready=regions_ready)
 
     def step_resident(s):
         """device-resident single-GPU step, no host sync (strict asserts off): source chain and target chain on two
@@ -274,16 +275,25 @@ def main():
 
     # multi-GPU: the batch is sharded by image; the only exchange is ONE all_gather of [prototype sums | counts | max id]
     # per step, kept outside the captured graphs (phase A: local statistics; phase B: fold + target chain + EMA)
+    # The region half of the target chain needs nothing global, so it runs in phase A, one step ahead: the rank-local
+    # max superpixel id falls out of the same pass as on one GPU (no second pass over the ids); one workspace per set.
+    ws_sets = [None] * args.sets
+
+    folded = [(torch.zeros((wl.c, wl.k), dtype=torch.float32, device=dev), torch.zeros(wl.c, dtype=torch.int64, device=dev),
+               torch.zeros(1, dtype=torch.int64, device=dev)) for _ in range(args.sets)]
+
     def phase_a(s, j):
         cur = torch.cuda.current_stream(dev)
-        sums, counts = source_stats(s)
-        mx = ops.i64_minmax(s["sup"])[1:]
+        partials = source_stats(s, fold=False)
+        mx = mining.region_phase(s["soft"], s["sup"], TEMP, R, ws_sets[j], wl.h, wl.w, wl.k)
         cur.wait_stream(side)
-        ops.pack_local(sums, counts, mx, out=packed_bufs[j])
+        ops.pack_local_partials(partials, mx, out=packed_bufs[j])   # image-order fold + pack in one launch
 
     def phase_b(s, j):
-        sums, counts, ignored = miner.fold(gathered_bufs[j])
-        out = target_chain(s, ignored)
+        # rank-ordered fold of the gathered statistics, one launch, captured with the rest of phase B (an eager launch
+        # behind the all_gather would take it off the GPU critical path but costs more host time per step than it saves)
+        sums, counts, ignored = ops.fold_gathered(gathered_bufs[j], wl.c, wl.k, out=folded[j])
+        out = target_chain(s, ignored, ws_sets[j], regions_ready=True)
         ops.proto_finalize(sums, counts, proto_state, eps=al.eps, decay=DECAY, want_local=False, out=proto_state)
         return out
 
@@ -300,6 +310,8 @@ def main():
     config.strict_asserts = False
     need = lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, R)
     ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+    if miner:
+        ws_sets = [torch.zeros(need, dtype=torch.uint8, device=dev) for _ in range(args.sets)]
     step_eager = step_sharded if miner else step_resident
 
     # ---- warm-up (eager), then graph capture: one graph (two around the exchange when sharded) per buffer set

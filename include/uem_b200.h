@@ -38,6 +38,7 @@ extern "C" {
 #define UEM_VIEW_PROTO 1
 #define UEM_VIEW_PRED 2
 #define UEM_VIEW_SUP 4
+#define UEM_VIEW_REGIONS_READY 8 /* uem_mine_refine_select_f32 only: uem_mine_region_phase_f32 already ran on this ws */
 
 /* region reduce ops (torch_scatter.scatter reduce=..., alignment.py:187,245) */
 #define UEM_REDUCE_SUM 0
@@ -178,6 +179,13 @@ UEM_API int uem_label_refine_f32(int views, const float* simi, const float* pred
  * the class statistics table of `refined` is left at byte offset uem_mine_ws_stats_offset(...) of ws. */
 UEM_API int64_t uem_mine_ws_bytes(int b, int c, int H, int W, int h, int w, int k, int64_t R);
 UEM_API int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R);
+/* Multi-GPU form: the region half of the chain on its own.  It needs nothing global, so it can run one step
+ * ahead of the exchange; it leaves the per-region weights in ws and the rank-LOCAL max superpixel id (int64) at byte
+ * offset uem_mine_ws_maxid_offset(...).  uem_mine_refine_select_f32(views | UEM_VIEW_REGIONS_READY, ..., ignored_id =
+ * the batch-global max id) then skips the region pass. */
+UEM_API int64_t uem_mine_ws_maxid_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R);
+UEM_API int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
+                              int w, int k, float temp, void* ws, void* stream);
 UEM_API int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos,
                                const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                                int64_t R, const int64_t* ignored_id, const float* soft, int b, int c, int H,
@@ -249,6 +257,9 @@ UEM_API int uem_pcl_backward_f32(const float* feat, int b, int k, int64_t hw, in
  * every rank gets bit-identical sums (alignment.py:347-353) and the batch-global max id (alignment.py:241). */
 UEM_API int uem_pack_local_f64(const float* sums, const int64_t* counts, const int64_t* max_id, int c, int k, double* out,
                        void* stream);
+/* same, straight from the per-image partials uem_proto_accum_nchw_f32 leaves in its ws when sums == NULL (folded in
+ * image order with the same fp32 additions as the separate fold) */
+UEM_API int uem_pack_local_partials_f64(const void* ws, int b, int c, int k, const int64_t* max_id, double* out, void* stream);
 UEM_API int uem_fold_gathered_f64(const double* gathered, int world, int c, int k, float* sums, int64_t* counts,
                           int64_t* max_id, void* stream);
 

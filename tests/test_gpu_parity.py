@@ -701,3 +701,46 @@ def test_exchange_pack_and_fold_kernels(dev):
     _eq(gs, ws, "folded sums")
     _eq(gc, wc, "folded counts")
     _eq(gm, wm, "folded max id")
+
+
+def test_staged_region_phase_equals_fused_chain(dev):
+    """8e: region half of the chain run on its own (one step ahead of the exchange) + refine/select with
+    UEM_VIEW_REGIONS_READY give bit-identical results to the single fused call, leave the workspace clean (second
+    round on the same workspace), and expose the rank-local max superpixel id."""
+    from uemda_b200 import mining
+    from uemda_b200.synth import WORKLOADS, make_inputs
+    wl = WORKLOADS["tiny"]
+    for seed in (3, 4):
+        inp = _to(make_inputs(wl, seed=seed), dev)
+        R = int(inp["ignore_id"]) + 1
+        kw = dict(feat=inp["feat"], prototypes=inp["prototypes"], pred1=inp["pred1"], pred2=inp["pred2"], sup=inp["sup"],
+                  num_regions=R, select=(0.8, 0.6, -1), uvem=(0.2, 0.7, 4.0))
+        want = mining.refine_select(7, inp["soft"], 2.0, **kw)
+        if seed == 3:
+            ws = mining.mine_workspace(inp["soft"], R, wl.h, wl.w, wl.k)
+        local = mining.region_phase(inp["soft"], inp["sup"], 2.0, R, ws, wl.h, wl.w, wl.k)
+        assert int(local.item()) == int(inp["sup"].max().item())
+        ignored = local.clone()   # a single rank: the global id is the local one
+        got = mining.refine_select(7, inp["soft"], 2.0, ignored_id=ignored, ws=ws, regions_ready=True, **kw)
+        for a, b2, name in zip(got, want, ("refined", "hard", "entropy", "uvem weight")):
+            _eq(a, b2, "staged " + name)
+        assert int(local.item()) == 0, "the selection kernel zeroes the max-id slot again"
+
+
+def test_pack_from_partials_equals_fold_then_pack(dev):
+    """8e: folding the per-image prototype partials and packing them in ONE launch is bit-identical to fold -> pack."""
+    from uemda_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    b, c, k, h, w = 5, 6, 96, 8, 12
+    feat = torch.randn(b, k, h, w, generator=g).to(dev)
+    lab = torch.randint(-1, c, (b, 1, h, w), generator=g).to(dev)
+    mx = torch.tensor([1234567], dtype=torch.int64, device=dev)
+    sums, counts = ops.proto_accumulate(feat, lab, c, -1)
+    want = ops.pack_local(sums, counts, mx)
+    got = ops.pack_local_partials(ops.proto_accumulate(feat, lab, c, -1, fold=False), mx)
+    _eq(got, want, "pack from partials")
+    out = (torch.empty((c, k), device=dev), torch.empty(c, dtype=torch.int64, device=dev), torch.empty(1, dtype=torch.int64, device=dev))
+    s2, c2, m2 = ops.fold_gathered(torch.stack([want, want]), c, k, out=out)
+    assert s2.data_ptr() == out[0].data_ptr()
+    _eq(c2, counts * 2, "folded counts into static buffers")
+    _eq(m2, mx, "folded max id into static buffers")

@@ -51,6 +51,8 @@ SIGNATURES = {
     "uem_class_stats_decode_f32": (_I, [_P, _I, _I, _P, _P, _P]),
     "uem_mine_ws_bytes": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_ws_stats_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
+    "uem_mine_ws_maxid_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
+    "uem_mine_region_phase_f32": (_I, [_P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
     "uem_mine_refine_select_f32": (_I, [_I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F,
                                         _L, _P, _P, _P, _P, _P, _P, _P]),
     "uem_proto_weight_4pixel_f32": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _L, _F, _P, _P]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "uem_pcl_forward_f32": (_I, [_P, _I, _I, _L, _P, _I, _P, _L, _F, _P, _P, _P, _P]),
     "uem_pcl_backward_f32": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P]),
     "uem_pack_local_f64": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "uem_pack_local_partials_f64": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "uem_fold_gathered_f64": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "uem_uvem_loss_forward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "uem_uvem_loss_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -720,6 +720,40 @@ __global__ void __launch_bounds__(256) fold_gathered_kernel(const double* __rest
 }
 }  // namespace
 
+namespace {
+// per-image partials of proto_accumulate folded in image order (the same fp32 additions as proto_fold_kernel) and
+// packed in the same launch
+__global__ void __launch_bounds__(256) pack_partials_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial,
+                                                            const int64_t* __restrict__ max_id, int b, int ck, int c,
+                                                            double* __restrict__ out) {
+    const int n = ck + c + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i < ck) {
+            float s = 0.f;
+            for (int bi = 0; bi < b; ++bi) s += partial[(int64_t)bi * ck + i];
+            out[i] = (double)s;
+        } else if (i < ck + c) {
+            int64_t cnt = 0;
+            for (int bi = 0; bi < b; ++bi) cnt += cnt_partial[bi * c + (i - ck)];
+            out[i] = (double)cnt;
+        } else {
+            out[i] = (double)max_id[0];
+        }
+    }
+}
+}  // namespace
+
+// ws: the per-image partials uem_proto_accum_nchw_f32 leaves when called with sums == NULL
+extern "C" int uem_pack_local_partials_f64(const void* ws, int b, int c, int k, const int64_t* max_id, double* out, void* stream) {
+    UEM_REQUIRE(ws && max_id && out && b > 0 && c > 0 && k > 0, "uem_pack_local_partials_f64: bad arguments");
+    const float* partial = (const float*)ws;
+    const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
+    const int n = c * k + c + 1;
+    pack_partials_kernel<<<min(uem_div_up(n, 256), UEM_SMS), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, max_id, b, c * k, c, out);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int uem_pack_local_f64(const float* sums, const int64_t* counts, const int64_t* max_id, int c, int k, double* out,
                                   void* stream) {
     UEM_REQUIRE(sums && counts && max_id && out && c > 0 && k > 0, "uem_pack_local_f64: bad arguments");

@@ -1341,6 +1341,32 @@ extern "C" int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, i
     (void)H;
     return mine_layout(b, c, W, h, w, k, R).stats;
 }
+extern "C" int64_t uem_mine_ws_maxid_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R) {
+    (void)H;
+    return mine_layout(b, c, W, h, w, k, R).maxid;
+}
+
+static bool mine_selfclean(int views, int c, int64_t R) {
+    return (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)cp_of(c) * 4 + 1) + 64 <= 200 * 1024;
+}
+
+// Region half of the fused chain on its own (multi-GPU form): region maxima of soft -> per-region
+// superpixel-view weights, and the rank-LOCAL max superpixel id at byte offset uem_mine_ws_maxid_offset(...) of ws.
+// The batch-global id (all-gather / all-reduce MAX across ranks, alignment.py:241) is only needed by the refine kernel,
+// so this half can run one step ahead of the exchange; uem_mine_refine_select_f32 with UEM_VIEW_REGIONS_READY then skips
+// it.  Same workspace, same self-cleaning protocol (the selection kernel zeroes the max-id slot again).
+extern "C" int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
+                                         int w, int k, float temp, void* ws, void* stream) {
+    UEM_REQUIRE(ws && soft && sup && b > 0 && H > 0 && W > 0, "uem_mine_region_phase_f32: bad arguments");
+    UEM_REQUIRE(mine_selfclean(UEM_VIEW_SUP, c, R), "uem_mine_region_phase_f32: region capacity %lld does not fit the shared-memory table",
+                (long long)R);
+    char* base = (char*)ws;
+    const MineLayout L = mine_layout(b, c, W, h, w, k, R);
+    const int64_t HW = (int64_t)H * W;
+    return uem_region_max_f32(soft, (int64_t)c * HW, HW, sup, b, HW, c, R, (unsigned*)(base + L.region), (int64_t*)(base + L.maxid),
+                              (int*)base, (float*)(base + L.sw), (int*)(base + L.done), temp, (unsigned*)(base + L.stats), b * (c + 2),
+                              (cudaStream_t)stream);
+}
 
 // Side stream of the fused chain: the feature-map pass (Pearson similarity) and the soft/superpixel pass (region
 // maxima) are independent until the refine kernel, so they are forked onto two streams and joined with events
@@ -1377,6 +1403,8 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
                                           int64_t* hard, const float* uvem /* NULL or host {m,t,1/gamma,coef_left,coef_right} */,
                                           float* entropy, float* weight, void* ws, void* stream) {
     UEM_REQUIRE(ws && soft && refined, "uem_mine_refine_select_f32: bad arguments");
+    const bool regions_ready = (views & UEM_VIEW_REGIONS_READY) != 0;   // uem_mine_region_phase_f32 already ran on this ws
+    views &= ~UEM_VIEW_REGIONS_READY;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
     const MineLayout L = mine_layout(b, c, W, h, w, k, R);
@@ -1393,7 +1421,9 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     // by the allocator, then kept clean by every call) -- the region-max kernel clears the class statistics, its tail
     // zeroes the table rows and arrival counters again, the selection kernel zeroes the max-id slot -- so no memset
     // node sits on the critical path.  Every other configuration zeroes the region before and after the call.
-    const bool selfclean = (views & UEM_VIEW_SUP) && R > 0 && R * ((int64_t)cp_of(c) * 4 + 1) + 64 <= 200 * 1024;
+    const bool selfclean = mine_selfclean(views, c, R);
+    UEM_REQUIRE(!regions_ready || (selfclean && ignored_id), "uem_mine_refine_select_f32: UEM_VIEW_REGIONS_READY needs the superpixel view, "
+                "a region capacity that fits shared memory and the batch-global ignored id");
     if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));
     // fork: the feature pass runs on the side stream while the region-max pass (below) runs on the caller's stream
     SideStream* side = nullptr;
@@ -1411,7 +1441,9 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
         if (fork) UEM_CUDA(cudaEventRecord(side->join, side->stream));
     }
     bool own_maxid = false;
-    if (views & UEM_VIEW_SUP) {
+    if (regions_ready) {
+        own_maxid = true;   // the slot holds the rank-local id: the selection kernel zeroes it again
+    } else if (views & UEM_VIEW_SUP) {
         UEM_REQUIRE(sup && R > 0, "uem_mine_refine_select_f32: superpixel view needs sup and a region capacity R");
         own_maxid = (ignored_id == nullptr);
         // region maxima of soft, NCHW viewed as (b,N,c): class stride HW; the batch max id (alignment.py:241) comes out
@@ -1435,7 +1467,7 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     // the region-max kernel is only requested when nothing else sits between the two launches
     if (fork) UEM_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     if ((rc = launch_refine(views, simi, pred1, pred2, h, w, sup, table, 1, R, ignored_id, soft, b, c, H, W, temp, refined,
-                            stats, sw, st, selfclean, selfclean)))
+                            stats, sw, st, selfclean, selfclean && !regions_ready)))
         return rc;
     const bool select = hard || entropy || weight;
     if (select) {

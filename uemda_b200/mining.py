@@ -20,8 +20,34 @@ from . import _lib as L
 from . import ops
 
 
+def mine_workspace(soft, num_regions, h, w, k):
+    """Zero-initialised scratch of the fused chain for one batch shape (self-cleaning: allocate once, reuse)."""
+    b, c, H, W = soft.shape
+    need = L.bind(soft).uem_mine_ws_bytes(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(int(num_regions), 1))
+    return torch.zeros(max(int(need), 16), dtype=torch.uint8, device=soft.device)
+
+
+def region_phase(soft, sup, temp, num_regions, ws, h, w, k):
+    """The region half of the chain on its own (multi-GPU form): region maxima of ``soft`` -> superpixel-view weights in
+    ``ws``; returns the rank-LOCAL max superpixel id as a (1,) int64 view INTO ``ws`` (read it -- e.g. pack it for the
+    exchange -- before the matching ``refine_select(..., regions_ready=True)``, whose selection kernel zeroes the slot).
+    Nothing here needs the batch-global id, so this can run one step ahead of the exchange (alignment.py:241-258)."""
+    L.require_cuda(soft, sup, ws)
+    soft = L.f32c(soft.detach())
+    sup = L.i64c(sup.detach())
+    b, c, H, W = soft.shape
+    R = int(num_regions)
+    lib = L.bind(soft)
+    dims = (b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
+    assert ws.numel() >= lib.uem_mine_ws_bytes(*dims), "workspace too small: mining.mine_workspace(...)"
+    L.check(lib.uem_mine_region_phase_f32(L.ptr(sup), R, L.ptr(soft), b, c, H, W, dims[4], dims[5], dims[6], ops.f32(temp),
+                                          L.ptr(ws), L.stream_of(soft)))
+    off = lib.uem_mine_ws_maxid_offset(*dims)
+    return ws[off:off + 8].view(torch.int64)
+
+
 def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pred2=None, sup=None, num_regions=None,
-                  ignored_id=None, eps=1e-7, select=None, ws=None, uvem=None, want_entropy=False):
+                  ignored_id=None, eps=1e-7, select=None, ws=None, uvem=None, want_entropy=False, regions_ready=False):
     """Returns (refined (b,c,H,W) fp32, hard (b,H,W) int64 or None); with ``uvem``/``want_entropy`` the tuple
     grows to (refined, hard, entropy (b*H*W,) or None, uvem_weight (b*H*W,) or None), all from the same pass.
 
@@ -30,7 +56,8 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
     num_regions: capacity R of the region table (ids must lie in [0,R)); None -> read sup.max() back
         (one 8-byte device->host copy, like torch_scatter's ``int(index.max())+1``).
     ignored_id: optional (1,) int64 device tensor holding the batch-global max id (e.g. after an
-        all_reduce(MAX) across ranks); None -> computed from ``sup`` inside the call."""
+        all_reduce(MAX) across ranks); None -> computed from ``sup`` inside the call.
+    regions_ready: ``region_phase`` already ran on ``ws`` for this batch (needs ``num_regions``, ``ignored_id``, ``ws``)."""
     L.require_cuda(soft, feat, prototypes, pred1, pred2, sup, ignored_id)
     soft = L.f32c(soft.detach())
     b, c, H, W = soft.shape
@@ -76,6 +103,9 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
         if uvem is not None:
             wgt = torch.empty(b * H * W, dtype=torch.float32, device=soft.device)
             uv = (ctypes.c_float * 5)(*ops._uvem_coefs(*uvem))
+    if regions_ready:
+        assert num_regions is not None and ignored_id is not None and ws is not None and (views & ops.VIEW_SUP)
+        views = int(views) | 8   # UEM_VIEW_REGIONS_READY
     L.check(lib.uem_mine_refine_select_f32(
         int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
@@ -166,13 +196,14 @@ class ShardedMiner:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
     # ---- three-phase form
-    def local_stats(self, sup_local, feat_s_local, label_s_local, out=None):
+    def local_stats(self, sup_local, feat_s_local, label_s_local, out=None, local_max_id=None):
         """Rank-local [prototype sums | counts | max superpixel id] of this step -> fp64 vector (written into ``out``
-        when given).  Also returns the down-scaled source labels."""
+        when given).  Also returns the down-scaled source labels.  local_max_id: the (1,) int64 tensor ``region_phase``
+        returned for this batch (then no separate pass over the ids is needed)."""
         al = self.aligner
         down = al.downscale_gt(label_s_local)
         sums, counts = ops.proto_accumulate(feat_s_local, down, al.class_num, al.ignore_label)
-        mx = ops.i64_minmax(sup_local)[1:]
+        mx = local_max_id if local_max_id is not None else ops.i64_minmax(sup_local)[1:]
         if out is not None and sums.is_cuda:
             packed = ops.pack_local(sums, counts, mx, out=out)
         else:

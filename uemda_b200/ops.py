@@ -494,14 +494,32 @@ def pack_local(sums, counts, max_id, out=None):
     return out
 
 
-def fold_gathered(gathered, c, k):
-    """(world, c*k+c+1) float64 -> (sums (c,k) fp32, counts (c,) int64, max id (1,) int64), ranks folded in rank order."""
+def pack_local_partials(partials, max_id, out=None):
+    """Per-image partials of proto_accumulate(fold=False) folded in image order and packed with the max id in one launch."""
+    ws, (b, c, k) = partials
+    L.require_cuda(ws, max_id)
+    max_id = L.i64c(max_id.detach()).reshape(-1)
+    lib = L.bind(ws)
+    if out is None:
+        out = torch.empty(c * k + c + 1, dtype=torch.float64, device=ws.device)
+    assert out.dtype == torch.float64 and out.numel() == c * k + c + 1 and out.is_contiguous()
+    L.check(lib.uem_pack_local_partials_f64(L.ptr(ws), b, c, k, L.ptr(max_id), L.ptr(out), L.stream_of(ws)))
+    return out
+
+
+def fold_gathered(gathered, c, k, out=None):
+    """(world, c*k+c+1) float64 -> (sums (c,k) fp32, counts (c,) int64, max id (1,) int64), ranks folded in rank order.
+    out: optional (sums, counts, max_id) tensors to write into (static buffers for CUDA-graph replay)."""
     L.require_cuda(gathered)
     assert gathered.dtype == torch.float64 and gathered.is_contiguous() and gathered.shape[1] == c * k + c + 1
     lib = L.bind(gathered)
-    sums = torch.empty((c, k), dtype=torch.float32, device=gathered.device)
-    counts = torch.empty((c,), dtype=torch.int64, device=gathered.device)
-    max_id = torch.empty((1,), dtype=torch.int64, device=gathered.device)
+    if out is not None:
+        sums, counts, max_id = out
+        assert sums.dtype == torch.float32 and sums.numel() == c * k and counts.dtype == torch.int64 and max_id.dtype == torch.int64
+    else:
+        sums = torch.empty((c, k), dtype=torch.float32, device=gathered.device)
+        counts = torch.empty((c,), dtype=torch.int64, device=gathered.device)
+        max_id = torch.empty((1,), dtype=torch.int64, device=gathered.device)
     L.check(lib.uem_fold_gathered_f64(L.ptr(gathered), gathered.shape[0], c, k, L.ptr(sums), L.ptr(counts), L.ptr(max_id),
                                       L.stream_of(gathered)))
     return sums, counts, max_id
