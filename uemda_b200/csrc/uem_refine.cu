@@ -737,20 +737,26 @@ __device__ __forceinline__ float4 ldg_f4_l1(const float4* p) {
 #define UEM_REFINE_COL_MINB 4   // 128 registers: no spills for C <= 8 (5 resident CTAs spill and run 30% slower at C = 7)
 #endif
 
-template <int C, int NT, int NS>
-__global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_col_kernel(const RefineParams p, const int ncols_max) {
-    constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32;
+// VX = image columns per lane (1 or 2).  With VX = 2 a lane owns two adjacent columns: the per-row bookkeeping (loop,
+// prefetch cursor, row coordinate, store addressing) is shared by two pixels, their two dependent chains interleave,
+// shared-memory reads and global stores become 64-bit; the price is twice the column state (12*PC registers).
+template <int C, int NT, int NS, int VX>
+__global__ void __launch_bounds__(NT, ((VX == 2 ? 3 : UEM_REFINE_COL_MINB) * 128) / NT)
+refine_col_kernel(const RefineParams p, const int ncols_max) {
+    constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32, WC = 32 * VX;
     constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
-    constexpr uint32_t kWarpStage = 32u * (4u * C + 8u);         // bytes of one row of a warp's 32 columns
-    constexpr int NCHUNK = 8 * C + 16;                           // 16-byte chunks of it: 8 per soft plane + 16 of ids
+    constexpr uint32_t kPlane = (uint32_t)WC * 4u;               // bytes of one soft plane of a warp row
+    constexpr uint32_t kWarpStage = (uint32_t)WC * (4u * C + 8u);   // bytes of one row of a warp's WC columns
+    constexpr int CPP = WC / 4;                                  // 16-byte chunks per soft plane
+    constexpr int NCHUNK = CPP * C + WC / 2;                     // + the ids (2 per chunk)
     constexpr int NCP = (NCHUNK + 31) / 32;                      // cp.async per lane and row
     extern __shared__ __align__(128) unsigned char smem_col[];
     const int W = p.W, H = p.H, w = p.w, h = p.h;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t HW = (int64_t)H * W;
     const int hw_low = h * w;
-    const int nstrips = (W + NT - 1) / NT;
-    // shared memory: [warp][stage][C planes x 32 floats | 32 ids]  then  [warp][2 rows][ncols_max][TS] tap scratch
+    const int nstrips = (W + NT * VX - 1) / (NT * VX);
+    // shared memory: [warp][stage][C planes x WC floats | WC ids]  then  [warp][2 rows][ncols_max][TS] tap scratch
     unsigned char* const wstage = smem_col + (size_t)wid * NS * kWarpStage;
     float* const taps = reinterpret_cast<float*>(smem_col + (size_t)NW * NS * kWarpStage) + (size_t)wid * 2 * ncols_max * TS;
 
@@ -761,11 +767,11 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
     if (n <= 0) return;
     const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
 
-    // ---- prefetch side.  A row of the warp's 32 columns is NCHUNK 16-byte chunks (chunk k sits at byte 16k of the
-    // stage: planes are 128 bytes each, ids follow); lane l copies chunks l, l+32[, l+64] with cp.async.cg 16.
+    // ---- prefetch side.  A row of the warp's WC columns is NCHUNK 16-byte chunks (chunk k sits at byte 16k of the
+    // stage: the planes are contiguous, ids follow); lane l copies chunks l, l+32, ... with cp.async.cg 16.
     // The source pointer of each chunk advances by one image row per unit; recomputed when the strip changes.
     const uint32_t wstage_u32 = smem_u32(wstage) + (uint32_t)lane * 16u;
-    const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * 4u;
+    const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * (4u * VX);
     int ibs = bs0, iy = y0, ibs_cur = -1;
     const char* csrc[NCP];
     uint32_t cstride[NCP];
@@ -775,17 +781,17 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
     auto prefetch = [&](int stage) {
         if (ibs != ibs_cur) {
             const int bi = ibs / nstrips, s = ibs - bi * nstrips;
-            const int xw = s * NT + wid * 32;
+            const int xw = s * NT * VX + wid * WC;
 #pragma unroll
             for (int q = 0; q < NCP; ++q) {
                 const int k = lane + 32 * q;
-                if (k < 8 * C) {
-                    const int ci = k >> 3, x = xw + (k & 7) * 4;
+                if (k < CPP * C) {
+                    const int ci = k / CPP, x = xw + (k - ci * CPP) * 4;
                     cvalid[q] = x < W;
                     csrc[q] = reinterpret_cast<const char*>(p.soft + ((int64_t)bi * C + ci) * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
                     cstride[q] = (uint32_t)W * 4u;
                 } else {
-                    const int x = xw + (k - 8 * C) * 2;
+                    const int x = xw + (k - CPP * C) * 2;
                     cvalid[q] = (k < NCHUNK) && x < W;
                     csrc[q] = reinterpret_cast<const char*>(p.sup + (int64_t)bi * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
                     cstride[q] = (uint32_t)W * 8u;
@@ -815,13 +821,15 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
     const uint32_t Ru = (uint32_t)p.R;
 
     // column state: pre-scaled row-pair interpolants of the three maps (pairs of classes; padded slot -> e = 0)
-    float2 A[3][PC], D[3][PC];
+    float2 A[VX][3][PC], D[VX][3][PC];
     int cur_bs = -1, cur_i0 = -1, cur_b = -1;
-    int a0 = 0, a1 = 0, abase = 0, ncols = 1;
-    float l0x = 0.f, l1x = 0.f;
+    int a0[VX], a1[VX], abase = 0, ncols = 1;
+    float l0x[VX], l1x[VX];
+#pragma unroll
+    for (int v = 0; v < VX; ++v) { a0[v] = a1[v] = 0; l0x[v] = l1x[v] = 0.f; }
     bool active = false;
     const float* ob = nullptr;      // out + (bi*C)*HW
-    uint32_t x = 0;
+    uint32_t x = 0;                 // first of the lane's VX columns
     const float4* swb = nullptr;
 
     float cmax[C];
@@ -859,13 +867,16 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
                 if (cur_b >= 0 && p.stats) flush(cur_b);
                 cur_b = bi;
             }
-            const int xw = s * NT + wid * 32;
-            x = (uint32_t)(xw + lane);
-            active = (int)x < W;
-            const Lerp lx = make_lerp(active ? (int)x : W - 1, w, p.sx);
-            a0 = lx.i0; a1 = lx.i1; l0x = lx.l0; l1x = lx.l1;
-            abase = make_lerp(min(xw, W - 1), w, p.sx).i0;                 // warp-uniform: first low-res column
-            ncols = make_lerp(min(xw + 31, W - 1), w, p.sx).i1 - abase + 1;  // <= ncols_max
+            const int xw = s * NT * VX + wid * WC;
+            x = (uint32_t)(xw + lane * VX);
+            active = (int)x < W;     // W % 4 == 0 and x % VX == 0: the lane's columns are all inside or all outside
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
+                const Lerp lx = make_lerp(active ? (int)x + v : W - 1, w, p.sx);
+                a0[v] = lx.i0; a1[v] = lx.i1; l0x[v] = lx.l0; l1x[v] = lx.l1;
+            }
+            abase = make_lerp(min(xw, W - 1), w, p.sx).i0;                      // warp-uniform: first low-res column
+            ncols = make_lerp(min(xw + WC - 1, W - 1), w, p.sx).i1 - abase + 1;   // <= ncols_max
             ob = p.out + (int64_t)bi * C * HW;
             swb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
             cur_bs = bs;
@@ -873,9 +884,9 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
         }
         const Lerp ly = make_lerp(y, h, p.sy);
         if (ly.i0 != cur_i0) {
-            // new low-res row pair.  The warp's 32 columns span `ncols` low-res columns: their 2 x ncols x 3C values are
+            // new low-res row pair.  The warp's WC columns span `ncols` low-res columns: their 2 x ncols x 3C values are
             // fetched once per warp (lane -> (map, class)), pre-scaled by log2 e [/temp], and every lane then reads the
-            // four corners of its own column as 128-bit shared-memory loads and interpolates horizontally, once.
+            // four corners of each of its columns as 128-bit shared-memory loads and interpolates horizontally, once.
             cur_i0 = ly.i0;
             __syncwarp();
             if (lane < 3 * C) {
@@ -891,113 +902,134 @@ __global__ void __launch_bounds__(NT, (UEM_REFINE_COL_MINB * 128) / NT) refine_c
                 }
             }
             __syncwarp();
-            const float* t00 = taps + (a0 - abase) * TS;
-            const float* t01 = taps + (a1 - abase) * TS;
-            const float2 l0 = make_float2(l0x, l0x), l1 = make_float2(l1x, l1x);
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                float v00[CP], v01[CP], v10[CP], v11[CP];
-                load_tap<C>(t00 + m * CP, v00);
-                load_tap<C>(t01 + m * CP, v01);
-                load_tap<C>(t00 + ncols_max * TS + m * CP, v10);
-                load_tap<C>(t01 + ncols_max * TS + m * CP, v11);
+            for (int v = 0; v < VX; ++v) {
+                const float* t00 = taps + (a0[v] - abase) * TS;
+                const float* t01 = taps + (a1[v] - abase) * TS;
+                const float2 l0 = make_float2(l0x[v], l0x[v]), l1 = make_float2(l1x[v], l1x[v]);
 #pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    const bool pad = 2 * j + 1 >= C;   // odd class count: the last pair's second slot is padding
-                    const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
-                    const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
-                    const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
-                    const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
-                    float2 ta = UEM_FFMA2(l1, p01, UEM_FMUL2(l0, p00));
-                    const float2 tb = UEM_FFMA2(l1, p11, UEM_FMUL2(l0, p10));
-                    float2 td = UEM_FADD2(tb, make_float2(-ta.x, -ta.y));
-                    if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
-                    A[m][j] = ta;
-                    D[m][j] = td;
+                for (int m = 0; m < 3; ++m) {
+                    float v00[CP], v01[CP], v10[CP], v11[CP];
+                    load_tap<C>(t00 + m * CP, v00);
+                    load_tap<C>(t01 + m * CP, v01);
+                    load_tap<C>(t00 + ncols_max * TS + m * CP, v10);
+                    load_tap<C>(t01 + ncols_max * TS + m * CP, v11);
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        const bool pad = 2 * j + 1 >= C;   // odd class count: the last pair's second slot is padding
+                        const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
+                        const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
+                        const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
+                        const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
+                        float2 ta = UEM_FFMA2(l1, p01, UEM_FMUL2(l0, p00));
+                        const float2 tb = UEM_FFMA2(l1, p11, UEM_FMUL2(l0, p10));
+                        float2 td = UEM_FADD2(tb, make_float2(-ta.x, -ta.y));
+                        if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
+                        A[v][m][j] = ta;
+                        D[v][m][j] = td;
+                    }
                 }
             }
         }
         cp_async_wait_group<NS - 1>();   // this lane's chunks of row `it` have landed ...
         __syncwarp();                    // ... and so have the other lanes' (the row is read across lanes)
         if (active) {
-            const uint32_t rd = rd_base + (uint32_t)stage * kWarpStage;   // this lane's float of plane 0
-            int64_t rid;
-            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(rid) : "r"(rd + (uint32_t)lane * 4u + (uint32_t)C * 128u));
+            const uint32_t rd = rd_base + (uint32_t)stage * kWarpStage;   // this lane's first float of plane 0
+            int64_t rid[VX];
+            if constexpr (VX == 2)
+                asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(rid[0]), "=l"(rid[1]) : "r"(rd + (uint32_t)lane * 8u + (uint32_t)C * kPlane));
+            else
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(rid[0]) : "r"(rd + (uint32_t)lane * 4u + (uint32_t)C * kPlane));
             // superpixel view first (its gather is the only long-latency access of the row): multiplicative outside the
             // ignored id; the ignored id and any id outside [0,R) are redirected to the all-ones sentinel row R
-            const uint32_t lo = (uint32_t)rid, hi = (uint32_t)((uint64_t)rid >> 32);
-            const bool in_region = (hi == 0u) & (lo < Ru) & (lo != ign_lo);
-            const uint32_t r = in_region ? lo : Ru;
-            const float4* wp = swb + r * (uint32_t)(CP / 4);
-            float4 swv[CP / 4];
+            float4 swv[VX][CP / 4];
 #pragma unroll
-            for (int q = 0; q < CP / 4; ++q) swv[q] = ldg_f4_l1(wp + q);
-
-            const float2 t2 = make_float2(ly.l1, ly.l1);
-            float2 wgt2[PC];
-            {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
-                float2 z[PC];
+            for (int v = 0; v < VX; ++v) {
+                const uint32_t lo = (uint32_t)rid[v], hi = (uint32_t)((uint64_t)rid[v] >> 32);
+                const bool in_region = (hi == 0u) & (lo < Ru) & (lo != ign_lo);
+                const uint32_t r = in_region ? lo : Ru;
+                const float4* wp = swb + r * (uint32_t)(CP / 4);
 #pragma unroll
-                for (int j = 0; j < PC; ++j) z[j] = UEM_FFMA2(t2, D[0][j], A[0][j]);
-                const float S = exp2_shifted2<PC>(z);
-                const float rs = fmaf(-1e-7f, S, 1.0f);
-                const float2 rs2 = make_float2(rs, rs);
-#pragma unroll
-                for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FMUL2(z[j], rs2);
+                for (int q = 0; q < CP / 4; ++q) swv[v][q] = ldg_f4_l1(wp + q);
             }
-            {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7); the 0.5 of the mean is
-                // folded into the epsilon (q/(max q + 2e-7) == (q/2)/(max q/2 + 1e-7), exact power-of-two scaling)
-                float2 z[PC], z2[PC];
-#pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    z[j] = UEM_FFMA2(t2, D[1][j], A[1][j]);
-                    z2[j] = UEM_FFMA2(t2, D[2][j], A[2][j]);
-                }
-                const float S1 = exp2_shifted2<PC>(z);
-                const float S2 = exp2_shifted2<PC>(z2);
-                // q_c = e1_c/S1 + e2_c/S2, scaled through by S1*S2 (in [1, C^2]): no reciprocal of the two sums
-                const float2 h1v = make_float2(S2, S2), h2v = make_float2(S1, S1);
-                float mx = 0.f;
-#pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    z[j] = UEM_FFMA2(z[j], h1v, UEM_FMUL2(z2[j], h2v));
-                    mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
-                }
-                const float inv = rcp_approx(fmaf(2e-7f, S1 * S2, mx));
-                const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-                for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FFMA2(z[j], inv2, wgt2[j]);
-            }
-#pragma unroll
-            for (int q = 0; q < CP / 4; ++q) {
-                wgt2[2 * q] = UEM_FMUL2(wgt2[2 * q], make_float2(swv[q].x, swv[q].y));
-                if (2 * q + 1 < PC) wgt2[2 * q + 1] = UEM_FMUL2(wgt2[2 * q + 1], make_float2(swv[q].z, swv[q].w));
-            }
-            // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
-            float o[C];
+            float sv[C][VX];
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
-                float sv;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(rd + (uint32_t)ci * 128u));
-                o[ci] = ((ci & 1) ? wgt2[ci >> 1].y : wgt2[ci >> 1].x) * sv;
+                if constexpr (VX == 2)
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(sv[ci][0]), "=f"(sv[ci][1]) : "r"(rd + (uint32_t)ci * kPlane));
+                else
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv[ci][0]) : "r"(rd + (uint32_t)ci * kPlane));
             }
-            float ps[PC];   // pairwise tree: depth log2(C) instead of a chain of C dependent adds
+            const float2 t2 = make_float2(ly.l1, ly.l1);
+            float o[C][VX];
 #pragma unroll
-            for (int j = 0; j < PC; ++j) ps[j] = (2 * j + 1 < C) ? o[2 * j] + o[2 * j + 1] : o[2 * j];
+            for (int v = 0; v < VX; ++v) {
+                float2 wgt2[PC];
+                {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
+                    float2 z[PC];
 #pragma unroll
-            for (int st2 = 1; st2 < PC; st2 *= 2)
+                    for (int j = 0; j < PC; ++j) z[j] = UEM_FFMA2(t2, D[v][0][j], A[v][0][j]);
+                    const float S = exp2_shifted2<PC>(z);
+                    const float rs = fmaf(-1e-7f, S, 1.0f);
+                    const float2 rs2 = make_float2(rs, rs);
 #pragma unroll
-                for (int j = 0; j + st2 < PC; j += 2 * st2) ps[j] += ps[j + st2];
-            const float s = ps[0];
-            const float inv = rcp_approx(s + 1e-7f);
-            nanacc = fmaf(s, 0.f, nanacc);   // s*0 accumulates to NaN iff a row sum was inf/NaN
+                    for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FMUL2(z[j], rs2);
+                }
+                {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7); the 0.5 of the mean is
+                    // folded into the epsilon (q/(max q + 2e-7) == (q/2)/(max q/2 + 1e-7), exact power-of-two scaling)
+                    float2 z[PC], z2[PC];
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        z[j] = UEM_FFMA2(t2, D[v][1][j], A[v][1][j]);
+                        z2[j] = UEM_FFMA2(t2, D[v][2][j], A[v][2][j]);
+                    }
+                    const float S1 = exp2_shifted2<PC>(z);
+                    const float S2 = exp2_shifted2<PC>(z2);
+                    // q_c = e1_c/S1 + e2_c/S2, scaled through by S1*S2 (in [1, C^2]): no reciprocal of the two sums
+                    const float2 h1v = make_float2(S2, S2), h2v = make_float2(S1, S1);
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        z[j] = UEM_FFMA2(z[j], h1v, UEM_FMUL2(z2[j], h2v));
+                        mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
+                    }
+                    const float inv = rcp_approx(fmaf(2e-7f, S1 * S2, mx));
+                    const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) wgt2[j] = UEM_FFMA2(z[j], inv2, wgt2[j]);
+                }
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    wgt2[2 * q] = UEM_FMUL2(wgt2[2 * q], make_float2(swv[v][q].x, swv[v][q].y));
+                    if (2 * q + 1 < PC) wgt2[2 * q + 1] = UEM_FMUL2(wgt2[2 * q + 1], make_float2(swv[v][q].z, swv[v][q].w));
+                }
+                // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) o[ci][v] = ((ci & 1) ? wgt2[ci >> 1].y : wgt2[ci >> 1].x) * sv[ci][v];
+                float ps[PC];   // pairwise tree: depth log2(C) instead of a chain of C dependent adds
+#pragma unroll
+                for (int j = 0; j < PC; ++j) ps[j] = (2 * j + 1 < C) ? o[2 * j][v] + o[2 * j + 1][v] : o[2 * j][v];
+#pragma unroll
+                for (int st2 = 1; st2 < PC; st2 *= 2)
+#pragma unroll
+                    for (int j = 0; j + st2 < PC; j += 2 * st2) ps[j] += ps[j + st2];
+                const float s = ps[0];
+                const float inv = rcp_approx(s + 1e-7f);
+                nanacc = fmaf(s, 0.f, nanacc);   // s*0 accumulates to NaN iff a row sum was inf/NaN
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float ov = o[ci][v] * inv;
+                    o[ci][v] = ov;
+                    cmax[ci] = fmaxf(cmax[ci], ov);
+                    cmin = fminf(cmin, ov);
+                }
+            }
             const uint32_t idx = (uint32_t)y * (uint32_t)W + x;   // < 2^31: one plane of one image
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
-                const float v = o[ci] * inv;
-                cmax[ci] = fmaxf(cmax[ci], v);
-                cmin = fminf(cmin, v);
-                const_cast<float*>(ob + (int64_t)ci * HW)[idx] = v;
+                float* dst = const_cast<float*>(ob + (int64_t)ci * HW) + idx;
+                if constexpr (VX == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[ci][0], o[ci][1]);
+                else *dst = o[ci][0];
             }
         }
         if (++y == H) { y = 0; ++bs; }
@@ -1163,24 +1195,28 @@ static int launch_refine_tma(RefineParams p, cudaStream_t st, bool pdl, bool* do
 #ifndef UEM_REFINE_COL_NT
 #define UEM_REFINE_COL_NT 128
 #endif
+#ifndef UEM_REFINE_COL_VX
+#define UEM_REFINE_COL_VX 2
+#endif
 template <int C>
 static int launch_refine_col(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
-    constexpr int NT = UEM_REFINE_COL_NT, NS = UEM_REFINE_COL_NS;
+    // two columns per lane while their state fits 168 registers (c <= 6); 7 and 8 classes would spill: one column
+    constexpr int NT = UEM_REFINE_COL_NT, NS = UEM_REFINE_COL_NS, VX = (C <= 6) ? UEM_REFINE_COL_VX : 1;
     *done = false;
     constexpr float kL2E = 1.4426950408889634f;
     p.map_scale[0] = kL2E;
     p.map_scale[1] = p.map_scale[2] = (float)(1.4426950408889634 / (double)p.temp);
-    // low-res columns one warp's 32 image columns can span (+1 for the right neighbour)
-    int ncols_max = (int)(31.0f * p.sx) + 3;
+    // low-res columns one warp's 32*VX image columns can span (+1 for the right neighbour)
+    int ncols_max = (int)((32 * VX - 1) * p.sx) + 3;
     if (ncols_max > p.w) ncols_max = p.w;
-    const size_t smem = (size_t)NS * NT * (4 * C + 8) + (size_t)(NT / 32) * 2 * ncols_max * 3 * cp_of(C) * 4;
+    const size_t smem = (size_t)NS * NT * VX * (4 * C + 8) + (size_t)(NT / 32) * 2 * ncols_max * 3 * cp_of(C) * 4;
     if (smem > 100 * 1024 || (int64_t)p.H * p.W >= ((int64_t)1 << 31)) return 0;   // generic kernels take it
-    auto kernel = refine_col_kernel<C, NT, NS>;
+    auto kernel = refine_col_kernel<C, NT, NS, VX>;
     if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
     if (per_sm < 1) per_sm = 1;
-    const int nstrips = (p.W + NT - 1) / NT;
+    const int nstrips = (p.W + NT * VX - 1) / (NT * VX);
     const int64_t total = (int64_t)p.b * nstrips * p.H;
     const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
     cudaLaunchConfig_t cfg = {};
