@@ -106,19 +106,21 @@ __global__ void __launch_bounds__(256) logits_pass_kernel(const float* __restric
 // softmax exponent a bare EX2.  There is no full-resolution input at all: the kernel is bound by its stores
 // (4c + 16 bytes per pixel), which are 32-bit per lane and contiguous over the warp (full 128-byte lines).
 // ------------------------------------------------------------------------------------------------
-template <int C, int NM>
-__global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int b, int h,
-                                                            int w, int H, int W, float sy, float sx, float scale,
-                                                            float* __restrict__ soft, float* __restrict__ conf,
-                                                            float* __restrict__ entropy, int64_t* __restrict__ argmax,
-                                                            const int ncols_max) {
-    constexpr int NT = 128, CP = (C + 3) & ~3, PC = (C + 1) / 2, TS = NM * CP;
+// VX = image columns per lane (2 when the row width is even: 64-bit stores, shared per-row bookkeeping, two interleaved
+// dependent chains; 1 otherwise)
+template <int C, int NM, int VX>
+__global__ void __launch_bounds__(128, VX == 2 ? 4 : 5) logits_col_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int b,
+                                                                          int h, int w, int H, int W, float sy, float sx, float scale,
+                                                                          float* __restrict__ soft, float* __restrict__ conf,
+                                                                          float* __restrict__ entropy, int64_t* __restrict__ argmax,
+                                                                          const int ncols_max) {
+    constexpr int NT = 128, CP = (C + 3) & ~3, PC = (C + 1) / 2, TS = NM * CP, WC = 32 * VX;
     extern __shared__ __align__(16) float taps_all[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* const taps = taps_all + (size_t)wid * 2 * ncols_max * TS;
     const int64_t HW = (int64_t)H * W;
     const int hw_low = h * w;
-    const int nstrips = (W + NT - 1) / NT;
+    const int nstrips = (W + NT * VX - 1) / (NT * VX);
     const int64_t total = (int64_t)b * nstrips * H;
     const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
     const int n = (int)(U1 - U0);
@@ -126,22 +128,27 @@ __global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restr
     int bs = (int)(U0 / H), y = (int)(U0 - (int64_t)bs * H);
     const float* maps[2] = {x1, x2};
 
-    float2 A[NM][PC], D[NM][PC];
+    float2 A[VX][NM][PC], D[VX][NM][PC];
     int cur_bs = -1, cur_i0 = -1, bi = 0;
-    int a0 = 0, a1 = 0, abase = 0, ncols = 1;
-    float l0x = 0.f, l1x = 0.f;
+    int a0[VX], a1[VX], abase = 0, ncols = 1;
+    float l0x[VX], l1x[VX];
+#pragma unroll
+    for (int v = 0; v < VX; ++v) { a0[v] = a1[v] = 0; l0x[v] = l1x[v] = 0.f; }
     bool active = false;
     uint32_t x = 0;
     for (int it = 0; it < n; ++it) {
         if (bs != cur_bs) {        // new (image, strip): column geometry
             bi = bs / nstrips;
-            const int xw = (bs - bi * nstrips) * NT + wid * 32;
-            x = (uint32_t)(xw + lane);
-            active = (int)x < W;
-            const Lerp lx = make_lerp(active ? (int)x : W - 1, w, sx);
-            a0 = lx.i0; a1 = lx.i1; l0x = lx.l0; l1x = lx.l1;
+            const int xw = (bs - bi * nstrips) * NT * VX + wid * WC;
+            x = (uint32_t)(xw + lane * VX);
+            active = (int)x < W;   // VX == 2 only with an even W: both columns inside or both outside
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
+                const Lerp lx = make_lerp(active ? (int)x + v : W - 1, w, sx);
+                a0[v] = lx.i0; a1[v] = lx.i1; l0x[v] = lx.l0; l1x[v] = lx.l1;
+            }
             abase = make_lerp(min(xw, W - 1), w, sx).i0;
-            ncols = make_lerp(min(xw + 31, W - 1), w, sx).i1 - abase + 1;
+            ncols = make_lerp(min(xw + WC - 1, W - 1), w, sx).i1 - abase + 1;
             cur_bs = bs;
             cur_i0 = -1;
         }
@@ -161,43 +168,48 @@ __global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restr
                 }
             }
             __syncwarp();
-            const float* t00 = taps + (a0 - abase) * TS;
-            const float* t01 = taps + (a1 - abase) * TS;
-            const float2 l0 = make_float2(l0x, l0x), l1 = make_float2(l1x, l1x);
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                float v00[CP], v01[CP], v10[CP], v11[CP];
+            for (int v = 0; v < VX; ++v) {
+                const float* t00 = taps + (a0[v] - abase) * TS;
+                const float* t01 = taps + (a1[v] - abase) * TS;
+                const float2 l0 = make_float2(l0x[v], l0x[v]), l1 = make_float2(l1x[v], l1x[v]);
 #pragma unroll
-                for (int q = 0; q < CP / 4; ++q) {
-                    const float4 q00 = *reinterpret_cast<const float4*>(t00 + m * CP + 4 * q);
-                    const float4 q01 = *reinterpret_cast<const float4*>(t01 + m * CP + 4 * q);
-                    const float4 q10 = *reinterpret_cast<const float4*>(t00 + ncols_max * TS + m * CP + 4 * q);
-                    const float4 q11 = *reinterpret_cast<const float4*>(t01 + ncols_max * TS + m * CP + 4 * q);
-                    v00[4 * q] = q00.x; v00[4 * q + 1] = q00.y; v00[4 * q + 2] = q00.z; v00[4 * q + 3] = q00.w;
-                    v01[4 * q] = q01.x; v01[4 * q + 1] = q01.y; v01[4 * q + 2] = q01.z; v01[4 * q + 3] = q01.w;
-                    v10[4 * q] = q10.x; v10[4 * q + 1] = q10.y; v10[4 * q + 2] = q10.z; v10[4 * q + 3] = q10.w;
-                    v11[4 * q] = q11.x; v11[4 * q + 1] = q11.y; v11[4 * q + 2] = q11.z; v11[4 * q + 3] = q11.w;
-                }
+                for (int m = 0; m < NM; ++m) {
+                    float v00[CP], v01[CP], v10[CP], v11[CP];
 #pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    const bool pad = 2 * j + 1 >= C;
-                    const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
-                    const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
-                    const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
-                    const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
-                    float2 ta = __ffma2_rn(l1, p01, __fmul2_rn(l0, p00));
-                    const float2 tb = __ffma2_rn(l1, p11, __fmul2_rn(l0, p10));
-                    float2 td = __fadd2_rn(tb, make_float2(-ta.x, -ta.y));
-                    if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
-                    A[m][j] = ta;
-                    D[m][j] = td;
+                    for (int q = 0; q < CP / 4; ++q) {
+                        const float4 q00 = *reinterpret_cast<const float4*>(t00 + m * CP + 4 * q);
+                        const float4 q01 = *reinterpret_cast<const float4*>(t01 + m * CP + 4 * q);
+                        const float4 q10 = *reinterpret_cast<const float4*>(t00 + ncols_max * TS + m * CP + 4 * q);
+                        const float4 q11 = *reinterpret_cast<const float4*>(t01 + ncols_max * TS + m * CP + 4 * q);
+                        v00[4 * q] = q00.x; v00[4 * q + 1] = q00.y; v00[4 * q + 2] = q00.z; v00[4 * q + 3] = q00.w;
+                        v01[4 * q] = q01.x; v01[4 * q + 1] = q01.y; v01[4 * q + 2] = q01.z; v01[4 * q + 3] = q01.w;
+                        v10[4 * q] = q10.x; v10[4 * q + 1] = q10.y; v10[4 * q + 2] = q10.z; v10[4 * q + 3] = q10.w;
+                        v11[4 * q] = q11.x; v11[4 * q + 1] = q11.y; v11[4 * q + 2] = q11.z; v11[4 * q + 3] = q11.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        const bool pad = 2 * j + 1 >= C;
+                        const float2 p00 = make_float2(v00[2 * j], pad ? 0.f : v00[2 * j + 1]);
+                        const float2 p01 = make_float2(v01[2 * j], pad ? 0.f : v01[2 * j + 1]);
+                        const float2 p10 = make_float2(v10[2 * j], pad ? 0.f : v10[2 * j + 1]);
+                        const float2 p11 = make_float2(v11[2 * j], pad ? 0.f : v11[2 * j + 1]);
+                        float2 ta = __ffma2_rn(l1, p01, __fmul2_rn(l0, p00));
+                        const float2 tb = __ffma2_rn(l1, p11, __fmul2_rn(l0, p10));
+                        float2 td = __fadd2_rn(tb, make_float2(-ta.x, -ta.y));
+                        if (pad) { ta.y = -1e30f; td.y = 0.f; }   // EX2 gives exactly 0, never wins a max
+                        A[v][m][j] = ta;
+                        D[v][m][j] = td;
+                    }
                 }
             }
         }
         if (active) {
             const float2 t2 = make_float2(ly.l1, ly.l1);
-            float pr[C];
-            {
+            float pr[VX][C], best[VX], ent[VX];
+            int arg[VX];
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
                 float2 e[NM][PC];
                 float rs[NM];
 #pragma unroll
@@ -205,7 +217,7 @@ __global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restr
                     float mx = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < PC; ++j) {
-                        e[m][j] = __ffma2_rn(t2, D[m][j], A[m][j]);
+                        e[m][j] = __ffma2_rn(t2, D[v][m][j], A[v][m][j]);
                         mx = fmaxf(mx, fmaxf(e[m][j].x, e[m][j].y));
                     }
                     float2 acc;
@@ -225,42 +237,54 @@ __global__ void __launch_bounds__(128, 5) logits_col_kernel(const float* __restr
                 for (int j = 0; j < PC; ++j) {
                     float2 q = __fmul2_rn(e[0][j], make_float2(rs[0], rs[0]));
                     if (NM == 2) q = __ffma2_rn(e[1][j], make_float2(rs[1], rs[1]), q);
-                    pr[2 * j] = q.x;
-                    if (2 * j + 1 < C) pr[2 * j + 1] = q.y;
+                    pr[v][2 * j] = q.x;
+                    if (2 * j + 1 < C) pr[v][2 * j + 1] = q.y;
                 }
-            }
-            float best = -INFINITY;
-            int arg = 0;
+                best[v] = -INFINITY;
+                arg[v] = 0;
 #pragma unroll
-            for (int ci = 0; ci < C; ++ci) {   // first (lowest) index wins ties: torch.max / argmax
-                const bool gt = pr[ci] > best;
-                best = gt ? pr[ci] : best;
-                arg = gt ? ci : arg;
+                for (int ci = 0; ci < C; ++ci) {   // first (lowest) index wins ties: torch.max / argmax
+                    const bool gt = pr[v][ci] > best[v];
+                    best[v] = gt ? pr[v][ci] : best[v];
+                    arg[v] = gt ? ci : arg[v];
+                }
+                if (entropy) ent[v] = entropy_px<C>(pr[v]);   // balance.py:372; p==0 -> NaN like the reference
             }
             const uint32_t idx = (uint32_t)y * (uint32_t)W + x;
-            if (soft) {
-                float* sb = soft + (int64_t)bi * C * HW;
+            if constexpr (VX == 2) {   // idx is even and every plane base is 8-byte aligned (checked by the launcher)
+                if (soft) {
+                    float* sb = soft + (int64_t)bi * C * HW;
 #pragma unroll
-                for (int ci = 0; ci < C; ++ci) (sb + (int64_t)ci * HW)[idx] = pr[ci];
+                    for (int ci = 0; ci < C; ++ci) *reinterpret_cast<float2*>(sb + (int64_t)ci * HW + idx) = make_float2(pr[0][ci], pr[1][ci]);
+                }
+                if (conf) *reinterpret_cast<float2*>(conf + (int64_t)bi * HW + idx) = make_float2(best[0], best[1]);
+                if (entropy) *reinterpret_cast<float2*>(entropy + (int64_t)bi * HW + idx) = make_float2(ent[0], ent[1]);
+                if (argmax) stg_i64x2(argmax + (int64_t)bi * HW + idx, arg[0], arg[1]);
+            } else {
+                if (soft) {
+                    float* sb = soft + (int64_t)bi * C * HW;
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) (sb + (int64_t)ci * HW)[idx] = pr[0][ci];
+                }
+                if (conf) (conf + (int64_t)bi * HW)[idx] = best[0];
+                if (entropy) (entropy + (int64_t)bi * HW)[idx] = ent[0];
+                if (argmax) (argmax + (int64_t)bi * HW)[idx] = arg[0];
             }
-            if (conf) (conf + (int64_t)bi * HW)[idx] = best;
-            if (entropy) (entropy + (int64_t)bi * HW)[idx] = entropy_px<C>(pr);   // balance.py:372; p==0 -> NaN like the reference
-            if (argmax) (argmax + (int64_t)bi * HW)[idx] = arg;
         }
         if (++y == H) { y = 0; ++bs; }
     }
 }
 
-template <int C, int NM>
-static int launch_logits_col(const float* x1, const float* x2, int b, int h, int w, int H, int W, float sy, float sx, float temp,
-                             float* soft, float* conf, float* entropy, int64_t* argmax, cudaStream_t st, bool* done) {
+template <int C, int NM, int VX>
+static int launch_logits_col_vx(const float* x1, const float* x2, int b, int h, int w, int H, int W, float sy, float sx, float temp,
+                                float* soft, float* conf, float* entropy, int64_t* argmax, cudaStream_t st, bool* done) {
     *done = false;
     constexpr int CP = (C + 3) & ~3;
-    int ncols_max = (int)(31.0f * sx) + 3;
+    int ncols_max = (int)((32 * VX - 1) * sx) + 3;
     if (ncols_max > w) ncols_max = w;
     const size_t smem = (size_t)4 * 2 * ncols_max * NM * CP * 4;
     if (smem > 64 * 1024 || (int64_t)H * W >= ((int64_t)1 << 31)) return 0;
-    auto kernel = logits_col_kernel<C, NM>;
+    auto kernel = logits_col_kernel<C, NM, VX>;
     if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem));
@@ -271,12 +295,22 @@ static int launch_logits_col(const float* x1, const float* x2, int b, int h, int
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
             sms = UEM_SMS;
     }
-    const int64_t total = (int64_t)b * ((W + 127) / 128) * H;
+    const int64_t total = (int64_t)b * ((W + 128 * VX - 1) / (128 * VX)) * H;
     const int grid = (int)min(total, (int64_t)sms * per_sm);
     kernel<<<grid, 128, smem, st>>>(x1, x2, b, h, w, H, W, sy, sx, (float)(1.4426950408889634 / (double)temp), soft, conf, entropy,
                                     argmax, ncols_max);
     *done = true;
     return 0;
+}
+
+template <int C, int NM>
+static int launch_logits_col(const float* x1, const float* x2, int b, int h, int w, int H, int W, float sy, float sx, float temp,
+                             float* soft, float* conf, float* entropy, int64_t* argmax, cudaStream_t st, bool* done) {
+    // two columns per lane need 64-bit aligned rows: even W (then H*W and every plane offset are even) and aligned bases
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+    const bool pair = (W % 2 == 0) && al8(soft) && al8(conf) && al8(entropy) && (!argmax || uem_aligned16(argmax));
+    if (pair) return launch_logits_col_vx<C, NM, 2>(x1, x2, b, h, w, H, W, sy, sx, temp, soft, conf, entropy, argmax, st, done);
+    return launch_logits_col_vx<C, NM, 1>(x1, x2, b, h, w, H, W, sy, sx, temp, soft, conf, entropy, argmax, st, done);
 }
 
 // entropy (+ optional UVEM weight / gate / valid count) of a probability map (b,c,HW)
