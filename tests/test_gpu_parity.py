@@ -744,3 +744,37 @@ def test_pack_from_partials_equals_fold_then_pack(dev):
     assert s2.data_ptr() == out[0].data_ptr()
     _eq(c2, counts * 2, "folded counts into static buffers")
     _eq(m2, mx, "folded max id into static buffers")
+
+
+@pytest.mark.parametrize("regions,uniform_image", [(9001, False), (20000, False), (300, True)])
+def test_chain_region_capacity_paths(dev, regions, uniform_image):
+    """Region tables that do NOT fit shared memory (config 5's 16k regions take the global-table path with per-call
+    zeroing instead of the self-cleaning one), sparse ids, and an image that consists of the ignored id only."""
+    from oracle import uem_oracle as O
+    from uemda_b200 import mining
+    g = torch.Generator().manual_seed(regions)
+    b, c, H, W, h, w, k = 2, 6, 96, 128, 6, 8, 24
+    soft = torch.softmax(torch.randn(b, c, H, W, generator=g) * 2, dim=1)
+    sup = torch.randint(0, regions, (b, 1, H // 4, W // 4), generator=g).repeat_interleave(4, 2).repeat_interleave(4, 3)
+    sup[0, 0, :3, :] = regions - 1                       # make sure the batch max (the ignored id) is present
+    if uniform_image:
+        sup[1] = regions - 1                             # image 1: every pixel carries the ignored id
+    feat = torch.randn(b, k, h, w, generator=g)
+    protos = torch.randn(c, k, generator=g)
+    p1 = torch.randn(b, c, h, w, generator=g) * 2
+    p2 = torch.randn(b, c, h, w, generator=g) * 2
+    want = O.label_refine(sup, feat, [p1, p2], soft, protos, mode="all", temp=2.0)
+    want_hard = O.pseudo_select(want)
+    kw = dict(feat=feat.to(dev), prototypes=protos.to(dev), pred1=p1.to(dev), pred2=p2.to(dev), sup=sup.to(dev),
+              select=(0.8, 0.6, -1))
+    for nr in (None, regions):
+        got, hard = mining.refine_select(7, soft.to(dev), 2.0, num_regions=nr, **kw)
+        assert_close(got, want, rtol=RTOL, atol=1e-7, what="refined, %d regions (capacity %s)" % (regions, nr))
+        mism = int((hard.cpu() != want_hard).sum())
+        assert mism <= 2, "label mismatches %d" % mism
+    # same workspace twice (the non-self-cleaning path must leave it clean as well)
+    ws = mining.mine_workspace(soft.to(dev), regions, h, w, k)
+    a = mining.refine_select(7, soft.to(dev), 2.0, num_regions=regions, ws=ws, **kw)
+    b2 = mining.refine_select(7, soft.to(dev), 2.0, num_regions=regions, ws=ws, **kw)
+    _eq(a[0], b2[0], "workspace reuse, refined")
+    _eq(a[1], b2[1], "workspace reuse, hard")
