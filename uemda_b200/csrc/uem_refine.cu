@@ -896,9 +896,20 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
                 float* dst = taps + m * CP + ci;
                 const float* r0 = plane + ly.i0 * w;
                 const float* r1 = plane + ly.i1 * w;
-                for (int j = 0; j < ncols; ++j) {
-                    dst[j * TS] = __ldg(r0 + j) * sc;
-                    dst[(ncols_max + j) * TS] = __ldg(r1 + j) * sc;
+                for (int j0 = 0; j0 < ncols; j0 += 4) {   // 8 loads in flight: one L2 round trip per 4 columns
+                    float u0[4], u1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = min(j0 + u, ncols - 1);
+                        u0[u] = __ldg(r0 + j);
+                        u1[u] = __ldg(r1 + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u < ncols) {
+                            dst[(j0 + u) * TS] = u0[u] * sc;
+                            dst[(ncols_max + j0 + u) * TS] = u1[u] * sc;
+                        }
                 }
             }
             __syncwarp();

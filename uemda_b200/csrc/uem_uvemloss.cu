@@ -76,9 +76,20 @@ __global__ void __launch_bounds__(128, 5) uvem_ce_col_kernel(const float* __rest
                 float* dst = taps + m * CP + ci;
                 const float* r0 = plane + ly.i0 * w;
                 const float* r1 = plane + ly.i1 * w;
-                for (int j = 0; j < ncols; ++j) {
-                    dst[j * TS] = __ldg(r0 + j) * kL2E;
-                    dst[(ncols_max + j) * TS] = __ldg(r1 + j) * kL2E;
+                for (int j0 = 0; j0 < ncols; j0 += 4) {   // 8 loads in flight: one L2 round trip per 4 columns
+                    float u0[4], u1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = min(j0 + u, ncols - 1);
+                        u0[u] = __ldg(r0 + j);
+                        u1[u] = __ldg(r1 + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u < ncols) {
+                            dst[(j0 + u) * TS] = u0[u] * kL2E;
+                            dst[(ncols_max + j0 + u) * TS] = u1[u] * kL2E;
+                        }
                 }
             }
             __syncwarp();
