@@ -8,21 +8,19 @@
 // Compulsory traffic per pixel: read soft (4c) + sup (8), write refined (4c); everything else (three
 // low-res maps, the per-region weight table) is L2/L1 resident.
 //
-// Kernel shape (round-1 ncu: the first version was issue-bound at 752 instr/pixel and ran 1.7 waves, so this one
-// is built to minimise instructions and to have no tail):
-//   * persistent CTAs of 128 threads, one contiguous range of image rows each (grid = SMs x resident CTAs);
-//   * a thread = 4 consecutive pixels; the soft tile and the superpixel ids go global->shared with cp.async
-//     (no registers held while the weights are computed) and are read back by the same thread;
-//   * per row the low-res maps are interpolated vertically once into shared memory, class-interleaved
-//     ([x'][map][class padded to 4]) so a tap is two LDS.128;
-//   * softmax followed by "/ (max + 1e-7)" collapses algebraically: max_c softmax = 1/S, hence
-//     w_c = e_c / (1 + 1e-7*S) = e_c * (1 - 1e-7*S) to O(1e-13): no division; exp is one MUFU (ex2.approx.ftz);
-//   * the default configuration (all views, two heads, >=3x up-sampling) runs a branch-free 3-tap form with
-//     packed fp32x2 math (FFMA2/FMUL2/FADD2, new on sm_100): class pairs share an instruction;
-//   * the superpixel view depends only on (image, region): softmax(/temp)/max of the region maxima is
-//     precomputed per region by a tiny kernel, the pixel kernel just gathers 2 x LDG.128;
-//   * per-(image,class) maxima for pseudo_selection (pseudo_generation.py:76) fall out as a (b, c+2) stats
-//     table updated with one atomicMax per class per CTA.
+// Two kernels:
+//   * refine_col_kernel -- the default configuration (all three views, two heads, W % 4 == 0): a lane owns one or two
+//     image COLUMNS and walks down a range of rows, so the horizontal half of the bilinear interpolation is hoisted out
+//     of the row loop (one packed FFMA per class pair and row); rows arrive by per-warp cp.async three rows ahead; no
+//     barrier in the row loop.  See the comment above the kernel and DESIGN.md section 3 for the measurements that led
+//     here (a row-major 4-pixels-per-thread TMA kernel with a 3-tap table, 37 us, was the previous default).
+//   * refine_kernel -- any view subset / one head / ragged or unaligned rows: persistent CTAs of 128 threads over image
+//     rows, a thread = 4 (or 1) consecutive pixels, low-res maps interpolated vertically once per row into shared memory.
+// Shared by both: softmax followed by "/ (max + 1e-7)" collapses algebraically (max_c softmax = 1/S, hence
+// w_c = e_c * (1 - 1e-7*S) to O(1e-13)): no division, exp is one MUFU (ex2.approx.ftz); the superpixel view depends only
+// on (image, region): softmax(/temp)/max of the region maxima is precomputed per region (by the region-max kernel's tail
+// on the fused chain), the pixel kernels gather 2 x LDG.128; per-(image,class) maxima for pseudo_selection
+// (pseudo_generation.py:76) fall out as a (b, c+2) stats table raised with atomicMax.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
 
@@ -36,10 +34,6 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
 int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw, float cutoff_top,
                                   float cutoff_low, int64_t ignore_label, int64_t* out, const float* uvem, float* entropy,
                                   float* weight, int64_t* zero_after, int pdl, cudaStream_t st);
-
-#ifndef UEM_REFINE_MINB
-#define UEM_REFINE_MINB 4   // resident 128-thread CTAs per SM the TMA kernel is compiled for (register cap = 64K/(128*MINB))
-#endif
 
 #define UEM_FFMA2(a, b, c) __ffma2_rn(a, b, c)
 #define UEM_FMUL2(a, b) __fmul2_rn(a, b)
@@ -121,17 +115,6 @@ template <int C> __device__ __forceinline__ void load_tap(const float* col, floa
         t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
     }
 }
-template <int C>
-__device__ __forceinline__ void load_tap3p(const float* col, int stride, float2 (&t)[3][Lay<C>::PC]) {
-#pragma unroll
-    for (int k3 = 0; k3 < 3; ++k3)
-#pragma unroll
-        for (int q = 0; q < Lay<C>::CP / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(col + k3 * stride + 4 * q);
-            t[k3][2 * q] = make_float2(v.x, v.y);
-            if (2 * q + 1 < Lay<C>::PC) t[k3][2 * q + 1] = make_float2(v.z, v.w);
-        }
-}
 
 // vertical lerp of the low-res rows feeding output row y into row[(w+2)][STRIDE]:
 // warp -> (map, class slot), lane -> low-res column: coalesced loads, no integer division by runtime values.
@@ -193,10 +176,10 @@ __device__ __forceinline__ void flush_stats(unsigned* stats, int bi, float (&cma
 }
 
 // Generic form: any view subset / one head / scalar path / any scale (2-tap scalar math, runtime view flags).
-// The default configuration (all views, two heads, 128-bit rows, >=3x up-sampling) runs refine_tma_kernel below.
+// The default configuration (all views, two heads, W % 4 == 0) runs refine_col_kernel below.
 template <int C, int VEC>
 __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefineParams p) {
-    constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE, PC = Lay<C>::PC;
+    constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* row = reinterpret_cast<float*>(smem_raw);                                        // [w+2][STRIDE]
     float* soft_s = row + (size_t)(p.w + 2) * STRIDE;                                       // [C][threads][VEC]
@@ -368,346 +351,6 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const RefinePara
         }
     }
     if (cur_b >= 0 && p.stats) flush_stats<C>(p.stats, cur_b, cmax, cmin, bad, red);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Default configuration (all three views, two heads, W % 4 == 0, >= 3x up-sampling): TMA-fed persistent kernel.
-//   * one CTA = 128 threads = one contiguous range of image rows; a thread = 4 consecutive pixels;
-//   * the soft rows (C class planes) and the superpixel-id row of a whole image row are brought in by the TMA
-//     engine: C+1 cp.async.bulk copies issued by one thread, completion on an mbarrier, NSTAGE rows in flight per
-//     CTA (no per-thread address math, no staging registers, 16 KB per row in flight at config 2);
-//   * the low-res maps (1/dist, two logit heads) of the NEXT row are fetched with 4-byte cp.async into a raw buffer
-//     while the current row is computed, then interpolated vertically into a double-buffered tap row
-//     (pre-scaled by log2(e) [/temp] so the softmax exponent is a bare EX2): one __syncthreads per row;
-//   * horizontal interpolation weights (3-tap form: same products and roundings as PyTorch's 2-tap lerp) depend
-//     on the column only and are tabulated once per CTA;
-//   * class pairs share packed fp32x2 instructions (FFMA2/FMUL2/FADD2);
-//   * the superpixel view is a branch-free gather of 2 x LDG.128 from the per-region weight table (ignored /
-//     out-of-range ids redirect to an all-ones sentinel row).
-// ------------------------------------------------------------------------------------------------
-// horizontal 3-tap weights of 4-pixel group g: column a = i0 of the first pixel; pixel i uses (a, a+1) with weights
-// (l0, l1, 0) or (a+1, a+2) with (0, l0, l1): the same products and roundings as PyTorch's 2-tap lerp
-template <int C>
-__device__ __forceinline__ void xtab_entry(float4* e, int g, int w, float sx) {
-    const int x0 = g * 4;
-    const int a = make_lerp(x0, w, sx).i0;
-    float wa[4], wb[4], wc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const Lerp lx = make_lerp(x0 + i, w, sx);
-        const bool d = lx.i0 != a;
-        wa[i] = d ? 0.f : lx.l0;
-        wb[i] = d ? lx.l0 : lx.l1;
-        wc[i] = d ? lx.l1 : 0.f;
-    }
-    e[0] = make_float4(__int_as_float(a * Lay<C>::STRIDE), 0.f, 0.f, 0.f);
-    e[1] = make_float4(wa[0], wa[1], wa[2], wa[3]);
-    e[2] = make_float4(wb[0], wb[1], wb[2], wb[3]);
-    e[3] = make_float4(wc[0], wc[1], wc[2], wc[3]);
-}
-// compact form (32 bytes per group, used when the full table would cost a resident CTA): column offset, a 4-bit mask of
-// the pixels that sit in the second interval, and the four l1; l0 = 1 - l1 is recomputed exactly as make_lerp does
-template <int C>
-__device__ __forceinline__ void xtab_entry_compact(float4* e, int g, int w, float sx) {
-    const int x0 = g * 4;
-    const int a = make_lerp(x0, w, sx).i0;
-    float l1[4];
-    int mask = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const Lerp lx = make_lerp(x0 + i, w, sx);
-        l1[i] = lx.l1;
-        mask |= (lx.i0 != a) << i;
-    }
-    e[0] = make_float4(__int_as_float(a * Lay<C>::STRIDE), __int_as_float(mask), l1[0], l1[1]);
-    e[1] = make_float4(l1[2], l1[3], 0.f, 0.f);
-}
-
-struct TmaLayout {
-    uint32_t stage_bytes, off_row, off_xt, off_raw, off_bar, total;
-};
-__host__ __device__ inline TmaLayout tma_layout(int C, int W, int w, int nstage, int xc) {
-    const int CP = (C + 3) & ~3;
-    TmaLayout L;
-    L.stage_bytes = (uint32_t)W * (4u * C + 8u);
-    uint32_t n = (uint32_t)nstage * L.stage_bytes;
-    L.off_row = n; n += 2u * (uint32_t)(w + 2) * 3u * CP * 4u;
-    L.off_xt = n; n += (uint32_t)(W / 4) * (xc ? 32u : 64u);
-    L.off_raw = n; n += ((2u * 3u * C * (uint32_t)w * 4u) + 15u) & ~15u;
-    L.off_bar = n; n += 8u * (((uint32_t)nstage + 2u) & ~1u);  // full[nstage] + the raw-row barrier
-    L.total = n;
-    return L;
-}
-
-template <int C, int NSTAGE, int NT, int XC>
-__global__ void __launch_bounds__(NT, (UEM_REFINE_MINB * 128) / NT) refine_tma_kernel(const RefineParams p) {
-    constexpr int CP = Lay<C>::CP, STRIDE = Lay<C>::STRIDE, PC = Lay<C>::PC, NW = NT / 32;
-    constexpr float kL2E = 1.4426950408889634f;
-    extern __shared__ __align__(128) unsigned char smem_tma[];
-    unsigned char* const smem_raw = smem_tma;
-    __shared__ float red[NW][C + 2];
-    const int W = p.W, w = p.w, H = p.H, groups = W >> 2;
-    const TmaLayout L = tma_layout(C, W, w, NSTAGE, XC);
-    float* rowbuf = reinterpret_cast<float*>(smem_raw + L.off_row);   // [2][w+2][STRIDE]
-    float4* xtab = reinterpret_cast<float4*>(smem_raw + L.off_xt);    // [groups][4]: {a, -, -, -}, wa[4], wb[4], wc[4] (or compact)
-    float* raw = reinterpret_cast<float*>(smem_raw + L.off_raw);      // [2][3C][w]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
-    const int rowlen = (w + 2) * STRIDE;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t HW = (int64_t)H * W;
-    const int hw_low = p.h * w;
-
-    const int64_t total_rows = (int64_t)p.b * H;
-    const int64_t R0 = total_rows * blockIdx.x / gridDim.x, R1 = total_rows * (blockIdx.x + 1) / gridDim.x;
-    const int nrows = (int)(R1 - R0);
-    if (nrows <= 0) return;
-    // ---- producer side (thread 0): one row = C soft planes + the id row
-    auto issue_row = [&](int64_t rr, int stage) {
-        const int bi = (int)(rr / H);
-        const int y = (int)(rr - (int64_t)bi * H);
-        unsigned char* dst = smem_raw + (size_t)stage * L.stage_bytes;
-        const float* src = p.soft + (int64_t)bi * C * HW + (int64_t)y * W;
-        mbar_arrive_expect_tx(&full[stage], L.stage_bytes);
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) tma_load_1d(dst + (size_t)ci * W * 4, src + (int64_t)ci * HW, (uint32_t)W * 4u, &full[stage]);
-        tma_load_1d(dst + (size_t)C * W * 4, p.sup + (int64_t)bi * HW + (int64_t)y * W, (uint32_t)W * 8u, &full[stage]);
-    };
-    // ---- low-res rows i0/i1 of the 3C planes feeding output row (bi,y): 2*3C bulk copies of w*4 bytes issued by the
-    // lanes of warp 0, only when (image, i0) changes (every ~H/h output rows); vertical lerp per output row below
-    uint64_t* rawbar = &full[NSTAGE];
-    int raw_bi = -1, raw_i0 = -1;
-    uint32_t raw_fetches = 0;   // CTA-uniform: completed + outstanding fetches
-    bool raw_pending = false;
-    auto fetch_lowres = [&](int fbi, int fy) {
-        const Lerp ly = make_lerp(fy, p.h, p.sy);
-        if (fbi == raw_bi && ly.i0 == raw_i0) return;
-        raw_bi = fbi;
-        raw_i0 = ly.i0;
-        ++raw_fetches;
-        raw_pending = true;
-        if (wid == 0) {
-            if (lane == 0) mbar_arrive_expect_tx(rawbar, 2u * 3u * C * (uint32_t)w * 4u);
-            if (lane < 3 * C) {
-                const int m = lane / C, ci = lane - m * C;
-                const float* plane = p.maps[m] + ((int64_t)fbi * C + ci) * hw_low;
-                tma_load_1d(raw + lane * w, plane + ly.i0 * w, (uint32_t)w * 4u, rawbar);
-                tma_load_1d(raw + (3 * C + lane) * w, plane + ly.i1 * w, (uint32_t)w * 4u, rawbar);
-            }
-        }
-    };
-    // thread -> (class ci = wid + NW*t, column x = lane + 32*s); map index and t are compile-time
-    auto lerp_lowres = [&](float* row, int ly_y) {
-        const Lerp ly = make_lerp(ly_y, p.h, p.sy);
-        if (raw_pending) { mbar_wait(rawbar, (raw_fetches - 1u) & 1u); raw_pending = false; }
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            const float sc = p.map_scale[m];
-            const bool dv = p.div_temp && m > 0;
-#pragma unroll
-            for (int t = 0; t < (C + NW - 1) / NW; ++t) {
-                const int ci = wid + NW * t;
-                if (ci < C) {
-                    const float* r0 = raw + (m * C + ci) * w;
-                    const float* r1 = r0 + 3 * C * w;
-                    float* d0 = row + m * CP + ci;
-                    for (int x = lane; x < w; x += 32) {
-                        const float v = ly.l0 * r0[x] + ly.l1 * r1[x];
-                        const float o = dv ? __fdiv_rn(v, p.temp) * kL2E : v * sc;
-                        float* d = d0 + x * STRIDE;
-                        d[0] = o;
-                        if (x == w - 1) { d[STRIDE] = o; d[2 * STRIDE] = o; }  // two replicated columns (tap a+2 always exists)
-                    }
-                }
-            }
-        }
-    };
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s <= NSTAGE; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();  // barriers initialised
-    int bi = (int)(R0 / H), y = (int)(R0 - (int64_t)bi * H);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE && s < nrows; ++s) issue_row(R0 + s, s);  // inputs only: safe before the dependency wait
-    }
-    // padded class slots: -1e30 -> EX2 gives exactly 0, never wins a max (written once, both tap rows)
-    if constexpr (CP > C) {
-        for (int i = threadIdx.x; i < 2 * (w + 2) * 3 * (CP - C); i += NT) {
-            const int slot = i % (CP - C), rest = i / (CP - C);
-            const int m = rest % 3, col = rest / 3;  // col runs over both buffers
-            rowbuf[col * STRIDE + m * CP + C + slot] = -1e30f;
-        }
-    }
-    for (int g = threadIdx.x; g < groups; g += NT) {
-        if constexpr (XC) xtab_entry_compact<C>(xtab + 2 * g, g, w, p.sx);
-        else xtab_entry<C>(xtab + 4 * g, g, w, p.sx);
-    }
-    // programmatic dependent launch: everything above touched only this kernel's inputs and its own shared memory;
-    // the similarity map, the region weights and the ignored id are produced by the preceding kernels
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    fetch_lowres(bi, y);
-    const int64_t ignored_id = *p.ignored_id;
-    // ids that take the all-ones sentinel row R: the ignored id (alignment.py:255) and anything outside [0,R)
-    const uint32_t ign_lo = ((uint64_t)ignored_id >> 32) == 0 ? (uint32_t)ignored_id : 0xffffffffu;
-    lerp_lowres(rowbuf, y);
-    __syncthreads();
-
-    float cmax[C];
-#pragma unroll
-    for (int ci = 0; ci < C; ++ci) cmax[ci] = -INFINITY;
-    float cmin = INFINITY;
-    bool bad = false;
-
-    for (int it = 0; it < nrows; ++it) {
-        const int stage = it % NSTAGE;
-        const uint32_t parity = (uint32_t)(it / NSTAGE) & 1u;
-        const float* row = rowbuf + (it & 1) * rowlen;
-        // next row's coordinates + its low-res fetch (in flight during this row's math)
-        int nbi = bi, ny = y + 1;
-        if (ny == H) { ny = 0; ++nbi; }
-        const bool has_next = it + 1 < nrows;
-        if (has_next) fetch_lowres(nbi, ny);
-        mbar_wait(&full[stage], parity);  // this row's soft planes + ids have landed (issued NSTAGE rows ago)
-
-        const float* soft_s = reinterpret_cast<const float*>(smem_raw + (size_t)stage * L.stage_bytes);
-        const longlong2* ids_s = reinterpret_cast<const longlong2*>(soft_s + (size_t)C * W);
-        float* outb = p.out + (int64_t)bi * C * HW + (int64_t)y * W;
-        const float4* swb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
-        const uint32_t Ru = (uint32_t)p.R;
-        float nanacc = 0.f;  // s*0 accumulates to NaN iff a row sum was inf/NaN
-        for (int g = threadIdx.x; g < groups; g += NT) {
-            float wa[4], wb[4], wc[4];
-            int col_off;
-            if constexpr (XC) {
-                const float4 e0 = xtab[g * 2], e1 = xtab[g * 2 + 1];
-                col_off = __float_as_int(e0.x);
-                const int mask = __float_as_int(e0.y);
-                const float l1[4] = {e0.z, e0.w, e1.x, e1.y};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float l0 = 1.0f - l1[i];
-                    const bool d = (mask >> i) & 1;
-                    wa[i] = d ? 0.f : l0;
-                    wb[i] = d ? l0 : l1[i];
-                    wc[i] = d ? l1[i] : 0.f;
-                }
-            } else {
-                const float4 q0 = xtab[g * 4], qa = xtab[g * 4 + 1], qb = xtab[g * 4 + 2], qc = xtab[g * 4 + 3];
-                col_off = __float_as_int(q0.x);
-                wa[0] = qa.x; wa[1] = qa.y; wa[2] = qa.z; wa[3] = qa.w;
-                wb[0] = qb.x; wb[1] = qb.y; wb[2] = qb.z; wb[3] = qb.w;
-                wc[0] = qc.x; wc[1] = qc.y; wc[2] = qc.z; wc[3] = qc.w;
-            }
-            const float* col = row + col_off;
-            float2 wgt2[PC][4];
-            {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
-                float2 t[3][PC];
-                load_tap3p<C>(col, STRIDE, t);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
-                    float2 z[PC];
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) z[j] = UEM_FFMA2(c2, t[2][j], UEM_FFMA2(b2, t[1][j], UEM_FMUL2(a2, t[0][j])));
-                    const float S = exp2_shifted2<PC>(z);
-                    const float rs = fmaf(-1e-7f, S, 1.0f);
-                    const float2 rs2 = make_float2(rs, rs);
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) wgt2[j][i] = UEM_FMUL2(z[j], rs2);
-                }
-            }
-            {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7).  The 0.5 of the mean is
-                // folded into the epsilon (q/(max q + 2e-7) == (q/2)/(max q/2 + 1e-7), exact power-of-two scaling)
-                float2 t[3][PC], u[3][PC];
-                load_tap3p<C>(col + CP, STRIDE, t);
-                load_tap3p<C>(col + 2 * CP, STRIDE, u);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 a2 = make_float2(wa[i], wa[i]), b2 = make_float2(wb[i], wb[i]), c2 = make_float2(wc[i], wc[i]);
-                    float2 z[PC], z2[PC];
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) {
-                        z[j] = UEM_FFMA2(c2, t[2][j], UEM_FFMA2(b2, t[1][j], UEM_FMUL2(a2, t[0][j])));
-                        z2[j] = UEM_FFMA2(c2, u[2][j], UEM_FFMA2(b2, u[1][j], UEM_FMUL2(a2, u[0][j])));
-                    }
-                    const float S1 = exp2_shifted2<PC>(z);
-                    const float S2 = exp2_shifted2<PC>(z2);
-                    const float h1 = rcp_approx(S1), h2 = rcp_approx(S2);
-                    const float2 h1v = make_float2(h1, h1), h2v = make_float2(h2, h2);
-                    float mx = 0.f;
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) {
-                        z[j] = UEM_FFMA2(z[j], h1v, UEM_FMUL2(z2[j], h2v));
-                        mx = fmaxf(mx, fmaxf(z[j].x, z[j].y));
-                    }
-                    const float inv = rcp_approx(mx + 2e-7f);
-                    const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) wgt2[j][i] = UEM_FFMA2(z[j], inv2, wgt2[j][i]);
-                }
-            }
-            // superpixel view: multiplicative outside the ignored id (branch-free: the ignored id and any id outside
-            // [0,R) are redirected to the all-ones sentinel row R)
-            {
-                const longlong2 i01 = ids_s[2 * g], i23 = ids_s[2 * g + 1];
-                const int64_t rid[4] = {i01.x, i01.y, i23.x, i23.y};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t lo = (uint32_t)rid[i], hi = (uint32_t)((uint64_t)rid[i] >> 32);
-                    const uint32_t r = (hi == 0u && lo < Ru && lo != ign_lo) ? lo : Ru;
-                    const float4* wp = swb + (size_t)r * (CP / 4);
-#pragma unroll
-                    for (int q = 0; q < CP / 4; ++q) {
-                        const float4 v = __ldg(wp + q);
-                        wgt2[2 * q][i] = UEM_FMUL2(wgt2[2 * q][i], make_float2(v.x, v.y));
-                        if (2 * q + 1 < PC) wgt2[2 * q + 1][i] = UEM_FMUL2(wgt2[2 * q + 1][i], make_float2(v.z, v.w));
-                    }
-                }
-            }
-            // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325)
-            float o[C][4];
-            {
-                const float* sp = soft_s + 4 * g;
-#pragma unroll
-                for (int ci = 0; ci < C; ++ci) {
-                    const float4 v = *reinterpret_cast<const float4*>(sp);
-                    sp += W;
-                    const float sv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) o[ci][i] = ((ci & 1) ? wgt2[ci >> 1][i].y : wgt2[ci >> 1][i].x) * sv[i];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float s = 0.f;
-#pragma unroll
-                for (int ci = 0; ci < C; ++ci) s += o[ci][i];
-                const float inv = rcp_approx(s + 1e-7f);
-                nanacc = fmaf(s, 0.f, nanacc);
-#pragma unroll
-                for (int ci = 0; ci < C; ++ci) o[ci][i] *= inv;
-            }
-            float* op = outb + 4 * g;
-#pragma unroll
-            for (int ci = 0; ci < C; ++ci) {
-                cmax[ci] = fmaxf(cmax[ci], fmaxf(fmaxf(o[ci][0], o[ci][1]), fmaxf(o[ci][2], o[ci][3])));
-                cmin = fminf(cmin, fminf(fminf(o[ci][0], o[ci][1]), fminf(o[ci][2], o[ci][3])));
-                stg_f4(op, make_float4(o[ci][0], o[ci][1], o[ci][2], o[ci][3]));
-                op += HW;
-            }
-        }
-        bad |= (nanacc != nanacc);
-        if (has_next) lerp_lowres(rowbuf + ((it + 1) & 1) * rowlen, ny);
-        __syncthreads();  // next tap row complete; everybody is done with this stage's soft/ids
-        if (threadIdx.x == 0 && it + NSTAGE < nrows) issue_row(R0 + it + NSTAGE, stage);
-        if (has_next && nbi != bi && p.stats) flush_stats<C>(p.stats, bi, cmax, cmin, bad, red);
-        bi = nbi;
-        y = ny;
-    }
-    if (p.stats) flush_stats<C>(p.stats, bi - (y == 0 ? 1 : 0), cmax, cmin, bad, red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1160,46 +803,7 @@ static int launch_persistent(K kernel, const RefineParams& p, int threads, size_
     return 0;
 }
 
-// TMA-fed kernel: NT = 128 threads for rows up to 512 pixels, 256 beyond (a row is one pass of the CTA);
-// two rows in flight per CTA unless a third fits without costing a resident CTA
-template <int C>
-static int launch_refine_tma(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
-    *done = false;
-    const int groups = p.W / 4;
-    const int nt = groups > 128 ? 256 : 128;
-    const size_t budget = 200 * 1024;
-    // resident CTAs per SM by shared memory (1 KB reserved per CTA) for {2,3} stages x {full, compact} column table
-    auto per_sm = [&](int nstage, int xc) -> size_t {
-        const size_t s = tma_layout(C, p.W, p.w, nstage, xc).total;
-        return s > budget ? 0 : (228 * 1024) / (s + 1024 + 256);
-    };
-    const size_t by_regs = (size_t)(UEM_REFINE_MINB * 128) / nt;  // what the register cap allows
-    if (per_sm(2, 1) == 0) return 0;  // row too long even for two stages: generic kernel
-    // the compact table only when the full one would cost a resident CTA; a third stage only when it is free
-    const int xc = (min(per_sm(2, 0), by_regs) < min(per_sm(2, 1), by_regs)) ? 1 : 0;
-    const bool three = per_sm(3, xc) >= min(per_sm(2, xc), by_regs) && per_sm(3, xc) > 0;
-    const size_t smem = tma_layout(C, p.W, p.w, three ? 3 : 2, xc).total;
-    constexpr float kL2E = 1.4426950408889634f;
-    p.map_scale[0] = kL2E;
-    p.map_scale[1] = p.map_scale[2] = kL2E / p.temp;  // used when temp is a power of two (exact scaling)
-    int rc;
-#define UEM_LAUNCH_TMA(NS, NTH, XCV) rc = launch_persistent(refine_tma_kernel<C, NS, NTH, XCV>, p, NTH, smem, st, pdl)
-    if (nt == 128) {
-        if (three) { if (xc) UEM_LAUNCH_TMA(3, 128, 1); else UEM_LAUNCH_TMA(3, 128, 0); }
-        else { if (xc) UEM_LAUNCH_TMA(2, 128, 1); else UEM_LAUNCH_TMA(2, 128, 0); }
-    } else {
-        if (three) { if (xc) UEM_LAUNCH_TMA(3, 256, 1); else UEM_LAUNCH_TMA(3, 256, 0); }
-        else { if (xc) UEM_LAUNCH_TMA(2, 256, 1); else UEM_LAUNCH_TMA(2, 256, 0); }
-    }
-#undef UEM_LAUNCH_TMA
-    *done = (rc == 0);
-    return rc;
-}
-
 // column-walk kernel: strips of 128 columns, 4 rows in flight per CTA
-#ifndef UEM_REFINE_COL
-#define UEM_REFINE_COL 1
-#endif
 #ifndef UEM_REFINE_COL_NS
 #define UEM_REFINE_COL_NS 4
 #endif
@@ -1282,8 +886,6 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     p.sup = sup; p.sw = sw_ws; p.R = R; p.ignored_id = ignored_id;
     p.soft = soft; p.out = out; p.stats = stats;
     const bool vec = (W % 4 == 0) && uem_aligned16(soft) && uem_aligned16(out) && (!sup || uem_aligned16(sup));
-    const bool fast = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2 && 3.0f * p.sx <= 0.999f &&
-                      (w % 4 == 0) && uem_aligned16(simi) && uem_aligned16(pred1) && uem_aligned16(pred2);
     // column-walk kernel: any up-sampling ratio, any low-res width
     const bool colwalk = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2;
     void *ev0 = nullptr, *ev1 = nullptr;
@@ -1298,8 +900,7 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
         bool done = false;
-        if (UEM_REFINE_COL && colwalk) rc = launch_refine_col<C>(p, st, pdl && weights_ready && !ev0, &done);
-        if (!done && rc == 0 && fast) rc = launch_refine_tma<C>(p, st, pdl && weights_ready && !ev0, &done);
+        if (colwalk) rc = launch_refine_col<C>(p, st, pdl && weights_ready && !ev0, &done);
         if (!done && rc == 0) {
             const int vecw = vec ? 4 : 1;
             const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
