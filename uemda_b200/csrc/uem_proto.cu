@@ -82,13 +82,15 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
 }
 
 // Power-of-two scale factors (the reference hard-wires 16): s/2 consecutive lanes own one output cell, each lane
-// streams its two columns over the s rows with independent 128-bit loads (16 in flight), and counts classes in packed
+// streams its two columns over the s rows with independent 128-bit loads (BR in flight), and counts classes in packed
 // 16-bit fields (two 64-bit registers hold bins 0..7, bin 8 separately), so a label costs a shift and an add instead
 // of C+1 compares.  The lanes of a cell fold their counters with xor-shuffles; lane 0 takes the first-index argmax.
-template <int C>
-__global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
-                                                             int64_t cells, int64_t ignore_label, float min_ratio,
-                                                             int64_t* __restrict__ out, int32_t* __restrict__ status) {
+// BR = rows per batch of independent loads: 16 (128 registers, 2 CTAs/SM: lowest latency when the whole grid is resident
+// at once) or 8 (3 CTAs/SM overlap their load and count phases: higher throughput on grids of several waves)
+template <int C, int BR>
+__device__ __forceinline__ void downscale_pow2_body(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
+                                                    int64_t cells, int64_t ignore_label, float min_ratio,
+                                                    int64_t* __restrict__ out, int32_t* __restrict__ status) {
     const int tpc = s >> 1;  // lanes per cell (1..32)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t cell = gid / tpc;
@@ -116,13 +118,13 @@ __global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __re
                 else ++b8;
             }
         };
-        for (int r0 = 0; r0 < s; r0 += 16) {
-            int64_t a[16], c2[16];
+        for (int r0 = 0; r0 < s; r0 += BR) {
+            int64_t a[BR], c2[BR];
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
+            for (int r = 0; r < BR; ++r)
                 if (r0 + r < s) ldg_i64x2(base + (int64_t)(r0 + r) * W, a[r], c2[r]);
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
+            for (int r = 0; r < BR; ++r)
                 if (r0 + r < s) { add(a[r]); add(c2[r]); }
         }
     }
@@ -143,6 +145,19 @@ __global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __re
         const float ratio = __fdiv_rn((float)best, (float)(s * s));  // avg_pool2d of the one-hot: count / (s*s)
         out[((int64_t)bi * h + oy) * w + ox] = (arg == C || ratio < min_ratio) ? ignore_label : (int64_t)arg;
     }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
+                                                             int64_t cells, int64_t ignore_label, float min_ratio,
+                                                             int64_t* __restrict__ out, int32_t* __restrict__ status) {
+    downscale_pow2_body<C, 16>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status);
+}
+template <int C>
+__global__ void __launch_bounds__(256, 3) downscale_pow2_stream_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h,
+                                                                       int w, int64_t cells, int64_t ignore_label, float min_ratio,
+                                                                       int64_t* __restrict__ out, int32_t* __restrict__ status) {
+    downscale_pow2_body<C, 8>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status);
 }
 
 // ------------------------------------------------------------------------------- prototype sums
@@ -573,8 +588,11 @@ extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W
         const int64_t cells = (int64_t)b * h * w;
         const int64_t threads = cells * (scale / 2);
         UEM_DISPATCH_C(n_classes, {
-            downscale_pow2_kernel<C><<<uem_div_up(threads, 256), 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out,
-                                                                             status);
+            const int nblk = uem_div_up(threads, 256);
+            if (nblk <= 2 * UEM_SMS)
+                downscale_pow2_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status);
+            else
+                downscale_pow2_stream_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status);
         });
         UEM_CHECK_LAUNCH();
         return 0;
