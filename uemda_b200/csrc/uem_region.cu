@@ -511,15 +511,25 @@ __global__ void __launch_bounds__(1024, 1) region_hist_smem_kernel(const int64_t
     // uniform trip count per warp: match.any needs the whole warp
     const int64_t span = g1 > g0 ? g1 - g0 : 0;
     const int64_t trips = (span + blockDim.x - 1) / blockDim.x;
+    // software pipeline: the loads of trip tr+1 are in flight while trip tr updates the table (the trips of a thread were
+    // one dependent DRAM round trip each)
+    int64_t nid[VEC], nlb[VEC];
+    auto fetch = [&](int64_t tr) {
+        const int64_t gg = g0 + tr * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { nid[i] = -1; nlb[i] = ignore_label; }
+        if (tr < trips && gg < g1) {
+            load_ids<VEC>(sp + gg * VEC, nid);
+            load_ids<VEC>(hd + gg * VEC, nlb);
+        }
+    };
+    fetch(0);
     for (int64_t tr = 0; tr < trips; ++tr) {
         const int64_t g = g0 + tr * blockDim.x + threadIdx.x;
         int64_t id[VEC], lb[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { id[i] = -1; lb[i] = ignore_label; }
-        if (g < g1) {
-            load_ids<VEC>(sp + g * VEC, id);
-            load_ids<VEC>(hd + g * VEC, lb);
-        }
+        for (int i = 0; i < VEC; ++i) { id[i] = nid[i]; lb[i] = nlb[i]; }
+        fetch(tr + 1);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const int64_t r = id[i], l = lb[i];
