@@ -361,10 +361,14 @@ def main():
         elif miner:
             for e in ev_b:
                 e.record(cur)
-            issue_ahead(first)
+            # look-ahead depth: with 3 buffer sets phase A + the all_gather run TWO steps ahead, so a late rank has a whole
+            # extra step before its contribution is needed (the buffers of step i+2 were last read by phase B of step i-1)
+            depth = max(1, min(2, args.sets - 1))
+            for i in range(first, min(first + depth, first + n)):
+                issue_ahead(i)
             for i in range(first, first + n):
-                if i + 1 < first + n:
-                    issue_ahead(i + 1)
+                if i + depth < first + n:
+                    issue_ahead(i + depth)
                 j = i % args.sets
                 cur.wait_event(ev_a[j])
                 graphs[j][1].replay()
