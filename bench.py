@@ -245,6 +245,8 @@ def main():
     packed_bufs = [torch.zeros(n_pack, dtype=torch.float64, device=dev) for _ in range(args.sets)]
     gathered_bufs = [torch.zeros((world, n_pack), dtype=torch.float64, device=dev) for _ in range(args.sets)]
     ahead = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    ev_p = [torch.cuda.Event() for _ in range(args.sets)]
     ev_a = [torch.cuda.Event() for _ in range(args.sets)]
     ev_b = [torch.cuda.Event() for _ in range(args.sets)]
 
@@ -345,13 +347,17 @@ def main():
             torch.cuda.synchronize()
 
     def issue_ahead(i):
-        """phase A + the all_gather of step i on the look-ahead stream"""
+        """phase A of step i on the look-ahead stream, its all_gather on a third stream: three pipeline stages
+        (A(i+2) | all_gather(i+1) | B(i)) so the collective's latency is not serialised behind the next phase A"""
         j = i % args.sets
         with torch.cuda.stream(ahead):
-            ahead.wait_event(ev_b[j])       # phase B that last read this buffer pair has finished
+            ahead.wait_event(ev_b[j])       # phase B that last read this buffer set has finished
             graphs[j][0].replay()
+            ev_p[j].record(ahead)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_p[j])
             miner.exchange(packed_bufs[j], out=gathered_bufs[j])
-            ev_a[j].record(ahead)
+            ev_a[j].record(comm)
 
     def run_steps(first, n):
         cur = torch.cuda.current_stream(dev)
