@@ -291,6 +291,23 @@ def main():
         cur.wait_stream(side)
         ops.pack_local_partials(partials, mx, out=packed_bufs[j])   # image-order fold + pack in one launch
 
+    # single GPU: the same two phases without the exchange.  Phase A (source statistics + region half of the target chain)
+    # reads neither the prototype bank nor anything phase B writes, so phase A of step i+1 overlaps phase B of step i:
+    # a software pipeline ACROSS steps (results identical to running the steps back to back).
+    partials_sets = [None] * args.sets
+    local_ids = [None] * args.sets
+
+    def phase_a1(s, j):
+        cur = torch.cuda.current_stream(dev)
+        partials_sets[j] = source_stats(s, fold=False)
+        local_ids[j] = mining.region_phase(s["soft"], s["sup"], TEMP, R, ws_sets[j], wl.h, wl.w, wl.k)
+        cur.wait_stream(side)
+
+    def phase_b1(s, j):
+        out = target_chain(s, local_ids[j], ws_sets[j], regions_ready=True)   # one rank: the local max id is the global one
+        ops.proto_fold_finalize(partials_sets[j], proto_state, eps=al.eps, decay=DECAY, out=proto_state)
+        return out
+
     def phase_b(s, j):
         # rank-ordered fold of the gathered statistics, one launch, captured with the rest of phase B (an eager launch
         # behind the all_gather would take it off the GPU critical path but costs more host time per step than it saves)
@@ -312,8 +329,7 @@ def main():
     config.strict_asserts = False
     need = lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, R)
     ws = torch.zeros(need, dtype=torch.uint8, device=dev)
-    if miner:
-        ws_sets = [torch.zeros(need, dtype=torch.uint8, device=dev) for _ in range(args.sets)]
+    ws_sets = [torch.zeros(need, dtype=torch.uint8, device=dev) for _ in range(args.sets)]
     step_eager = step_sharded if miner else step_resident
 
     # ---- warm-up (eager), then graph capture: one graph (two around the exchange when sharded) per buffer set
@@ -335,10 +351,12 @@ def main():
                         keep.append(phase_b(s, j))
                     graphs.append((ga, gb))
                 else:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=main_stream):
-                        keep.append(step_resident(s))
-                    graphs.append(g)
+                    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga, stream=main_stream):
+                        phase_a1(s, j)
+                    with torch.cuda.graph(gb, stream=main_stream):
+                        keep.append(phase_b1(s, j))
+                    graphs.append((ga, gb))
             barrier()
         except Exception as e:  # noqa: BLE001
             if rank == 0:
@@ -354,6 +372,9 @@ def main():
             ahead.wait_event(ev_b[j])       # phase B that last read this buffer set has finished
             graphs[j][0].replay()
             ev_p[j].record(ahead)
+            if not miner:
+                ev_a[j].record(ahead)
+                return
         with torch.cuda.stream(comm):
             comm.wait_event(ev_p[j])
             miner.exchange(packed_bufs[j], out=gathered_bufs[j])
@@ -364,7 +385,7 @@ def main():
         if graphs is None:
             for i in range(first, first + n):
                 step_eager(sets[i % args.sets])
-        elif miner:
+        else:
             for e in ev_b:
                 e.record(cur)
             # look-ahead depth: with 3 buffer sets phase A + the all_gather run TWO steps ahead, so a late rank has a whole
@@ -379,9 +400,6 @@ def main():
                 cur.wait_event(ev_a[j])
                 graphs[j][1].replay()
                 ev_b[j].record(cur)
-        else:
-            for i in range(first, first + n):
-                graphs[i % args.sets].replay()
 
 
     run_steps(0, args.warmup)
@@ -513,7 +531,10 @@ def main():
                        "regions": wl.regions, "step": "label_refine(all)+pseudo_selection+update_prototype+entropy/uvem_weight",
                        "l2_policy": "inputs rotate over %d buffer sets (%.0f MiB each) so each step reads cold data" % (
                            args.sets, sum(v.numel() * v.element_size() for v in sets[0].values()) / 2 ** 20),
-                       "cuda_graph": graphs is not None, "parallelism": "batch-sharded x%d" % world},
+                       "cuda_graph": graphs is not None, "parallelism": "batch-sharded x%d" % world,
+                       "pipeline": "two graphs per step: A = source statistics + region half of the target chain (reads no "
+                                   "prototype), B = pearson + refine + selection + EMA; A of step i+1/i+2 overlaps B of step i"
+                                   if graphs is not None else "none"},
             "step_algorithmic_bytes": chain_bytes,
             "step_hbm_frac": chain_bytes / (ms * 1e-3) / 1e9 / peak,
             "roofline": roof,
