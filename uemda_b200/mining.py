@@ -105,7 +105,7 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
             uv = (ctypes.c_float * 5)(*ops._uvem_coefs(*uvem))
     if regions_ready:
         assert num_regions is not None and ignored_id is not None and ws is not None and (views & ops.VIEW_SUP)
-        views = int(views) | 8   # UEM_VIEW_REGIONS_READY
+        views = int(views) | ops.VIEW_REGIONS_READY
     L.check(lib.uem_mine_refine_select_f32(
         int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
