@@ -333,7 +333,7 @@ def test_refine_column_kernel_shapes(dev, shape, temp):
                                   pred2=p2.to(dev), sup=sup.to(dev))
     assert_close(got, want, rtol=RTOL, atol=1e-7, what="refine column kernel %s temp=%s" % (shape, temp))
     # per-(image, class) maxima that feed pseudo_selection come out of the same pass
-    stats = got._uem_stats[0]
+    stats = got._uem_stats.stats
     hard = O.pseudo_select(got.cpu())
     from uemda_b200 import ops
     _eq(ops.pseudo_select_stats(got, stats, 0.8, 0.6, -1), hard, "selection from the kernel's own class statistics")
@@ -778,3 +778,114 @@ def test_chain_region_capacity_paths(dev, regions, uniform_image):
     b2 = mining.refine_select(7, soft.to(dev), 2.0, num_regions=regions, ws=ws, **kw)
     _eq(a[0], b2[0], "workspace reuse, refined")
     _eq(a[1], b2[1], "workspace reuse, hard")
+
+
+# ------------------------------------------------------------------------------------ round-2 regressions
+@pytest.mark.parametrize("mode", ["all", "s", "p", "l"])
+@pytest.mark.parametrize("num_regions", [None, "tight", 7000])
+def test_label_refine_then_selection_every_mode(golden, dev, mode, num_regions):
+    """label_refine(mode) -> pseudo_selection must equal pseudo_selection of a plain copy of the refined map (which takes
+    the two-pass class-max path) for every view subset and for region capacities on both sides of the shared-memory
+    table limit: the class statistics handed from the refine call to the selection must be those of THIS call on the
+    non-self-cleaning paths too ('p' / 'l' have no superpixel view; R = 7000 exceeds the table)."""
+    from uemda_b200.gast.pseudo_generation import pseudo_selection
+    g = golden
+    al = _aligner(g, dev)
+    if num_regions == "tight":
+        al.num_regions = g.ignore_id + 1
+    elif num_regions is not None:
+        al.num_regions = num_regions
+    preds = [p.to(dev) for p in g.preds()] if g.two_heads else g.preds().to(dev)
+    for _ in range(2):   # twice: the second call runs on whatever the first left behind
+        refined = al.label_refine(g.t("in_sup", dev), g.t("in_feat", dev), preds, g.t("in_soft", dev), mode=mode, temp=2.0)
+        assert_close(refined, g.t("out_refine_" + mode), rtol=RTOL, atol=1e-7, what="label_refine " + mode)
+        cached = pseudo_selection(refined, 0.8, 0.6, "tensor", -1)
+        plain = pseudo_selection(refined.clone(), 0.8, 0.6, "tensor", -1)
+        _eq(cached, plain, "selection with cached class statistics, mode %s, R %s" % (mode, num_regions))
+        assert int((plain != -1).sum()) > 0
+
+
+def test_stats_cache_is_not_trusted_blindly(golden, dev):
+    """The side-channel cache must not be used for a tensor it does not describe (in-place edit, other class count)."""
+    from uemda_b200.gast.pseudo_generation import pseudo_selection
+    g = golden
+    al = _aligner(g, dev)
+    preds = [p.to(dev) for p in g.preds()] if g.two_heads else g.preds().to(dev)
+    refined = al.label_refine(g.t("in_sup", dev), g.t("in_feat", dev), preds, g.t("in_soft", dev), mode="all", temp=2.0)
+    cache = refined._uem_stats
+    assert cache.valid_for(refined)
+    other = refined[:, : g.c - 1].contiguous()
+    other._uem_stats = cache                      # wrong class count
+    assert not cache.valid_for(other)
+    _eq(pseudo_selection(other, 0.8, 0.6, "tensor", -1), pseudo_selection(other.clone(), 0.8, 0.6, "tensor", -1), "foreign cache")
+    refined.mul_(0.5)                             # in-place edit bumps the version
+    assert not cache.valid_for(refined)
+    _eq(pseudo_selection(refined, 0.8, 0.6, "tensor", -1), pseudo_selection(refined.clone(), 0.8, 0.6, "tensor", -1), "stale cache")
+
+
+def test_out_of_range_ids_raise_under_strict_asserts(golden, dev):
+    """Superpixel ids outside [0, num_regions): the reference's scatter/gather raises; so does the drop-in under
+    strict_asserts (status word of the workspace read back and cleared)."""
+    from uemda_b200 import config
+    g = golden
+    al = _aligner(g, dev)
+    al.num_regions = 5   # far too small
+    preds = [p.to(dev) for p in g.preds()] if g.two_heads else g.preds().to(dev)
+    assert config.strict_asserts
+    with pytest.raises(RuntimeError):
+        al.label_refine(g.t("in_sup", dev), g.t("in_feat", dev), preds, g.t("in_soft", dev), mode="all", temp=2.0)
+    with pytest.raises(RuntimeError):
+        al.superpixel_expand(g.t("out_select_soft", dev), g.t("in_sup", dev))
+    neg = g.t("in_sup", dev).clone()
+    neg[0, 0, 0, 0] = -3
+    al.num_regions = None
+    with pytest.raises(RuntimeError):
+        al.label_refine(neg, g.t("in_feat", dev), preds, g.t("in_soft", dev), mode="s", temp=2.0)
+    al.num_regions = g.ignore_id + 1   # and a good call afterwards is clean
+    got = al.label_refine(g.t("in_sup", dev), g.t("in_feat", dev), preds, g.t("in_soft", dev), mode="all", temp=2.0)
+    assert_close(got, g.t("out_refine_all"), rtol=RTOL, atol=1e-7, what="label_refine after a rejected call")
+
+
+@pytest.mark.parametrize("hw", [(33, 33), (5, 7), (17, 2)])
+def test_pcl_loss_odd_feature_maps(dev, hw):
+    """4-D feature maps whose h*w is not a multiple of 4 (33x33, 65x65 decoders): the reference accepts any shape."""
+    from oracle import uem_oracle as O
+    from uemda_b200.loss import PrototypeContrastiveLoss
+    h, w = hw
+    g = torch.Generator().manual_seed(h * 100 + w)
+    b, k, c = 3, 64, 5
+    protos = torch.randn(c, k, generator=g)
+    lab = torch.randint(-1, c, (b, 1, h, w), generator=g)
+    feat = torch.randn(b, k, h, w, generator=g)
+    f_ref = feat.clone().requires_grad_(True)
+    want = O.pcl_loss(protos, f_ref, lab, temperature=8.0)
+    want.backward()
+    f = feat.to(dev).requires_grad_(True)
+    loss = PrototypeContrastiveLoss(8.0, -1)(protos.to(dev), f, lab.to(dev))
+    loss.backward()
+    assert_close(loss.detach().reshape(1), want.detach().reshape(1), rtol=RTOL, atol=1e-7, what="pcl loss odd map")
+    assert_close(f.grad, f_ref.grad, rtol=1e-4, atol=1e-5 * float(f_ref.grad.abs().max()), what="pcl grad odd map")
+
+
+def test_regeneration_run_reuses_buffers_and_streams(dev):
+    """PseudoLabelRegenerator.run over many small batches (double-buffered staging + two reused pinned output buffers):
+    every batch's output must equal process() of the same batch run on its own."""
+    from uemda_b200.gast.alignment import Aligner
+    from uemda_b200.regen import PseudoLabelRegenerator
+    from uemda_b200.synth import Workload, make_inputs
+    wl = Workload("regen2", 2, 6, 64, 64, 32, 16, 16)
+    batches = []
+    for i in range(7):
+        inp = make_inputs(wl, seed=100 + i, with_source=False)
+        batches.append({"soft": inp["soft"].pin_memory(), "sup": inp["sup"].pin_memory(), "feat": inp["feat"].pin_memory(),
+                        "preds": [inp["pred1"].pin_memory(), inp["pred2"].pin_memory()], "names": ["b%d_%d" % (i, j) for j in range(2)]})
+    al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c, decay=0.996)
+    al.prototypes = inp["prototypes"].to(dev)
+    regen = PseudoLabelRegenerator(al, 0.8, 0.6, mode="all", temp=2.0, num_regions=int(inp["ignore_id"]) + 1)
+    got = {}
+    n = regen.run(batches, lambda names, arr: got.update({nm: arr[j].copy() for j, nm in enumerate(names)}))
+    assert n == 14 and len(got) == 14
+    for i, bt in enumerate(batches):
+        want = regen.process(bt["soft"].to(dev), bt["sup"].to(dev), bt["feat"].to(dev), [p.to(dev) for p in bt["preds"]]).cpu().numpy()
+        for j in range(2):
+            assert (got["b%d_%d" % (i, j)] == want[j]).all(), "batch %d tile %d" % (i, j)

@@ -42,7 +42,7 @@ def main():
     for s in sets:
         s["refined"], _ = mining.refine_select(7, s["soft"], 2.0, feat=s["feat"], prototypes=protos, pred1=s["pred1"],
                                                pred2=s["pred2"], sup=s["sup"], num_regions=R)
-        s["stats"] = s["refined"]._uem_stats[0]
+        s["stats"] = s["refined"]._uem_stats.stats
         s["hard"] = ops.pseudo_select_stats(s["refined"], s["stats"], 0.8, 0.6, -1)
         s["simi"] = ops.pearson_dist_nchw(s["feat"], protos, reciprocal=True)
         s["rmax"] = ops.region_reduce(s["soft"], s["sup"], "max", dim_size=R, planar=True)

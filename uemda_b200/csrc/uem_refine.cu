@@ -1126,6 +1126,12 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
             return rc;
     }
     if (selfclean && own_maxid && !select) UEM_CUDA(cudaMemsetAsync(maxid, 0, 16, st));
-    if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));  // leave the block clean
+    if (!selfclean) {
+        // leave the block clean -- except the class statistics: the drop-in pairing label_refine -> pseudo_selection reads
+        // them after this call returns (mining.refine_select); every path clears them at entry (the memset above here,
+        // the region-max kernel on the self-cleaning path), so they need not be zero on exit
+        UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.stats - L.zero_begin), st));
+        UEM_CUDA(cudaMemsetAsync(base + L.region, 0, (size_t)(L.zero_end - L.region), st));
+    }
     return 0;
 }

@@ -10,8 +10,8 @@ __all__ = ["pseudo_selection", "pseudo_selection1"]
 def _class_max_checked(mask):
     """per-(b,c) max of `mask`; reproduces the reference's range assert (pseudo_generation.py:36,71)."""
     cached = getattr(mask, "_uem_stats", None)
-    if cached is not None and cached[1] == mask._version and cached[0].shape[0] == mask.shape[0]:
-        stats = cached[0]                        # (b, c+2) statistics table raised by the refine kernel
+    if cached is not None and cached.valid_for(mask):
+        stats = cached.stats                     # (b, c+2) statistics table raised by the refine kernel
         if config.strict_asserts:
             cmax, imin = ops.class_stats_decode(stats, mask.shape[1])
             host = torch.cat([cmax.reshape(-1), imin]).cpu()

@@ -24,7 +24,8 @@ class _PCLFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         feat, coef, ws = ctx.saved_tensors
-        return ops.pcl_backward(feat, coef, ws, grad_out), None, None, None, None
+        # the kernels compute in fp32; a half-precision feature map (autocast) gets its gradient back in its own dtype
+        return ops.pcl_backward(feat, coef, ws, grad_out).to(feat.dtype), None, None, None, None
 
 
 class PrototypeContrastiveLoss(nn.Module):
@@ -48,4 +49,13 @@ class PrototypeContrastiveLoss(nn.Module):
                 lab = torch.nn.functional.pad(lab, (0, pad), value=self.ignore_label)
             return _PCLFunction.apply(rows.contiguous(), Proto, lab, self.temperature, self.ignore_label)
         assert feat.dim() == 4
+        b, k, h, w = feat.shape
+        if (h * w) % 4:
+            # the TMA-tiled kernels need 16-byte aligned pixel rows: odd maps (33x33, 65x65) take the padded row form (all
+            # images as one row of b*h*w pixels, padding labelled ignore); the reference accepts any shape
+            n = b * h * w
+            pad = (-n) % 4
+            rows = torch.nn.functional.pad(feat.permute(1, 0, 2, 3).reshape(1, k, 1, n), (0, pad))
+            lab = torch.nn.functional.pad(labels.reshape(1, n), (0, pad), value=self.ignore_label)
+            return _PCLFunction.apply(rows.contiguous(), Proto, lab, self.temperature, self.ignore_label)
         return _PCLFunction.apply(feat, Proto, labels, self.temperature, self.ignore_label)

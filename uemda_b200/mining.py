@@ -17,7 +17,37 @@ import ctypes
 import torch
 
 from . import _lib as L
-from . import ops
+from . import config, ops
+
+
+class StatsCache:
+    """Class statistics of a refined map handed from label_refine to pseudo_selection (side channel on the tensor).
+    ``valid_for`` checks everything the selection kernel relies on, so a stale or foreign cache is never trusted."""
+    __slots__ = ("stats", "version", "b", "c", "device")
+
+    def __init__(self, stats, version, b, c, device):
+        self.stats, self.version, self.b, self.c, self.device = stats, version, b, c, device
+
+    def valid_for(self, mask):
+        return (mask.dim() == 4 and mask._version == self.version and mask.shape[0] == self.b and mask.shape[1] == self.c
+                and mask.device == self.device and mask.dtype == torch.float32 and self.stats.device == mask.device
+                and tuple(self.stats.shape) == (self.b, self.c + 2))
+
+
+def _raise_on_status(ws, what):
+    """The chain records ids it could not place in the status word at ws[0..3] (include/uem_b200.h): bit 2 = a superpixel
+    id outside [0, R) (such pixels are routed to the all-ones sentinel row, i.e. NOT refined by the superpixel view).
+    The reference's scatter / gather raises on those (alignment.py:245-250), so under config.strict_asserts this does too
+    (one 4-byte device->host read); the word is cleared so a persistent workspace does not carry stale bits.  With
+    strict_asserts off nothing is read back: out-of-range ids silently take the sentinel row."""
+    word = ws[:4].view(torch.int32)
+    bits = int(word.item())
+    if bits:
+        word.zero_()
+        if bits & 2:
+            raise RuntimeError("%s: superpixel id outside [0, num_regions) (index out of bounds in the reference's "
+                               "scatter/gather, alignment.py:245-250); raise Aligner.num_regions" % what)
+        raise RuntimeError("%s: label outside {ignore} U [0, class_num)" % what)
 
 
 def mine_workspace(soft, num_regions, h, w, k):
@@ -110,11 +140,14 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
         int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
         L.ptr(hard), uv, L.ptr(ent), L.ptr(wgt), L.ptr(ws), L.stream_of(soft)))
+    if config.strict_asserts:
+        _raise_on_status(ws, "label_refine")
     # [class maxima | -min | bad] of `refined`, reused by pseudo_selection() so it needs no second max pass
     if select is None:  # the drop-in pairing label_refine -> pseudo_selection: hand the class statistics over
+        # (every path of the C call leaves the table of THIS call in the workspace: uem_refine.cu, end of the chain)
         off = lib.uem_mine_ws_stats_offset(b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
         stats = ws[off:off + b * (c + 2) * 4].view(torch.int32).view(b, c + 2).clone()
-        refined._uem_stats = (stats, refined._version)
+        refined._uem_stats = StatsCache(stats, refined._version, b, c, refined.device)
     if want_entropy or uvem is not None:
         return refined, hard, ent, wgt
     return refined, hard

@@ -10,6 +10,7 @@ import struct
 import torch
 
 from . import _lib as L
+from . import config
 
 VIEW_PROTO, VIEW_PRED, VIEW_SUP = 1, 2, 4
 VIEW_REGIONS_READY = 8  # uem_mine_refine_select_f32 only: mining.region_phase already ran on the workspace
@@ -221,6 +222,16 @@ def superpixel_expand(hard, sup, class_num, ignore_label=-1, num_regions=None):
     ws = L.workspace(lib.uem_superpixel_expand_ws_bytes(b, R, class_num), hard)
     L.check(lib.uem_superpixel_expand_i64(L.ptr(hard), L.ptr(sup), b, N, class_num, R, int(ignore_label), L.ptr(out),
                                           L.ptr(ws), L.stream_of(hard)))
+    if config.strict_asserts:
+        # status word behind [counts | winner] (uem_region.cu): pixels with an id outside [0,R) or a label outside
+        # {ignore} U [0,c) were skipped; the reference's one_hot / scatter / gather raise on them (alignment.py:184-190)
+        off = (b * R * class_num + b * R) * 4
+        bits = int(ws[off:off + 4].view(torch.int32).item())
+        if bits & 1:
+            raise RuntimeError("Class values must be non-negative and smaller than num_classes.")
+        if bits & 2:
+            raise RuntimeError("superpixel_expand: superpixel id outside [0, num_regions) (index out of bounds in the "
+                               "reference's scatter/gather, alignment.py:187-190)")
     return out
 
 

@@ -82,14 +82,16 @@ class PseudoLabelRegenerator:
     def run(self, batches, sink, rank=0, world_size=1, device=None):
         """batches: a sequence of dicts {'soft', 'sup', 'feat', 'preds', 'names'} of HOST (ideally pinned) or device
         tensors; this rank processes the contiguous slice mining.shard_range(len(batches), rank, world_size).
-        sink(names, uint8 ndarray (b,H,W)) is called once per finished batch (the copy back is double-buffered).
-        Returns the number of tiles processed by this rank."""
+        sink(names, uint8 ndarray (b,H,W)) is called once per finished batch; the array lives in one of two reused pinned
+        buffers and is only valid during the call (copy what must be kept).  Input staging and the copy back are
+        double-buffered.  Returns the number of tiles processed by this rank."""
         device = device or torch.device("cuda", torch.cuda.current_device())
         lo, hi = mining.shard_range(len(batches), rank, world_size)
         copy_stream = torch.cuda.Stream(device=device)
         cur = torch.cuda.current_stream(device)
         pending = []
         done = 0
+        host_bufs = [None, None]   # pinned output buffers, reused (batch j uses buffer j % 2; at most two are in flight)
 
         def to_dev(x):
             if x is None:
@@ -97,6 +99,17 @@ class PseudoLabelRegenerator:
             if isinstance(x, (list, tuple)):
                 return [to_dev(y) for y in x]
             return x.to(device, non_blocking=True)
+
+        def hand_over(x):
+            # tensors staged under copy_stream are consumed by kernels on `cur`: tell the caching allocator, or their blocks
+            # return to copy_stream's pool while the chain may still be reading them (the next staging would overwrite them)
+            if x is None:
+                return
+            if isinstance(x, (list, tuple)):
+                for y in x:
+                    hand_over(y)
+            elif x.is_cuda:
+                x.record_stream(cur)
 
         staged = None
         for i in range(lo, hi + 1):
@@ -111,8 +124,13 @@ class PseudoLabelRegenerator:
                     nxt["ready"] = ev
             if staged is not None:
                 cur.wait_event(staged["ready"])
+                for k in ("soft", "sup", "feat", "preds"):
+                    hand_over(staged[k])
                 u8 = self.process(staged["soft"], staged["sup"], staged["feat"], staged["preds"])
-                host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+                j = (i - 1 - lo) % 2
+                if host_bufs[j] is None or host_bufs[j].shape != u8.shape:
+                    host_bufs[j] = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+                host = host_bufs[j]
                 host.copy_(u8, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cur)
