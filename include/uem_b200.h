@@ -263,6 +263,39 @@ UEM_API int uem_pack_local_partials_f64(const void* ws, int b, int c, int k, con
 UEM_API int uem_fold_gathered_f64(const double* gathered, int world, int c, int k, float* sums, int64_t* counts,
                           int64_t* max_id, void* stream);
 
+/* ---- device-side exchange over peer-mapped memory (csrc/uem_exchange.cu) -------------------------------
+ * The same statistics as above, but stored by a kernel straight into every peer's symmetric region over NVLink, with
+ * release/acquire flags instead of a host-issued collective, so a whole sharded step is capturable as CUDA graphs with no
+ * NCCL call between them.  Per-rank vector: [c*k prototype sums f32 | c counts i64 | c+1 class histogram i64 (balance.py:
+ * 45-52; zeros when hist == NULL) | rank-local max superpixel id i64 (alignment.py:241)].
+ * region: uem_xchg_region_bytes(world, depth, c, k) bytes per rank, ZEROED before the first use (then a barrier across
+ *   ranks), mapped into every peer (torch symmetric memory or uem_peer_*); peer_regions: HOST array of `world` device
+ *   pointers, entry r = rank r's region as mapped in THIS process (entry `rank` = the local region).
+ * depth <= 4 slots are used round-robin by the caller (slot = step % depth); world <= 16.
+ * send: folds the per-image partials uem_proto_accum_nchw_f32 left in partials_ws (sums == NULL form) in image order and
+ *   stores the vector into slot [slot][rank] of every peer; waits (bounded) for the peers' acknowledgement of the
+ *   previous use of that slot first.
+ * wait_maxid: blocks the stream (bounded spin in a one-warp kernel) until every rank's vector of this slot has arrived;
+ *   writes the batch-global max id.  fold_finalize_ema: (after wait_maxid on the same stream) folds the ranks in rank
+ *   order -> keep-old rule -> EMA (alignment.py:347-353,463-466; proto_new may alias proto_old; NULL = no EMA), optional
+ *   folded sums (c,k) / counts (c) / histogram (c+1) outputs; acknowledges the slot to every peer.
+ * uem_xchg_status: synchronises the stream and returns the region's status word: bit 8 = a spin timed out (2 s; a peer
+ *   is gone or the calls are not issued in lockstep), bit 16 = fold_finalize ran before its vectors had arrived. */
+UEM_API int64_t uem_xchg_region_bytes(int world, int depth, int c, int k);
+UEM_API int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
+                      const void* const* peer_regions, int rank, int world, int depth, int slot, void* stream);
+UEM_API int uem_xchg_wait_maxid(void* region, int world, int depth, int slot, int c, int k, int64_t* max_id_out, void* stream);
+UEM_API int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, int rank, int world, int depth, int slot, int c,
+                                   int k, const float* proto_old, float eps, float one_minus_decay, float decay,
+                                   float* proto_new, float* sums_out, int64_t* counts_out, int64_t* hist_out, void* stream);
+UEM_API int uem_xchg_status(const void* region, int* status_out, void* stream);
+/* cudaIpc plumbing for the region when torch symmetric memory is unavailable: alloc (cudaMalloc + zero) returns the local
+ * pointer and a 64-byte handle to ship to the peers (any host channel), open maps a peer's handle. */
+UEM_API int uem_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+UEM_API int uem_peer_open(const void* handle64, void** ptr);
+UEM_API int uem_peer_close(void* ptr);
+UEM_API int uem_peer_free(void* ptr);
+
 /* ---- UVEM / UPS target loss fused end to end, forward + backward (next row) ----------
  * uemda/gast/balance.py:437-457 (loss_calc_uvem: every head's logits up-sampled bilinearly, align_corners=True, to the
  * label size; loss averaged over heads), :356-394 (UVEMLoss.forward), :321-342 (UPSLoss.forward).

@@ -13,10 +13,11 @@ shimmed:
     (matplotlib, ttach, ever, skimage, uemda.viz, uemda.datasets) -> empty stubs.
   * ``Tensor.cuda`` -> identity (the container has no GPU).
 
-This file only works where /root/reference exists (the build container).  It is
-used by ``oracle/gen_golden.py`` to produce ``tests/golden/*.npz`` and by the
-CPU tests that cross-check ``oracle/uem_oracle.py`` against the reference when
-the tree is present.  Nothing that runs on the GPU box imports it.
+It needs the reference's modules: the tree under /root/reference (the build container) or,
+where that is absent (the GPU box), their byte-compiled form under oracle/_ref (oracle/build_ref.py).
+It is used by ``oracle/gen_golden*.py`` to produce ``tests/golden/*.npz``, by the CPU tests that
+cross-check ``oracle/uem_oracle.py`` against the reference, and by ``bench.py``'s CPU legs
+(``--impl reference``, ``cpu_baseline``) to time the reference's own functions on the host cores.
 """
 import importlib
 import os
@@ -25,11 +26,31 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("UEM_REFERENCE_ROOT", "/root/reference")
+_SRC_ROOT = os.environ.get("UEM_REFERENCE_ROOT", "/root/reference")
+_BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (sourceless .pyc)
+
+
+def _pick_root():
+    if os.path.isdir(os.path.join(_SRC_ROOT, "uemda", "gast")):
+        return _SRC_ROOT
+    if os.path.exists(os.path.join(_BUILT_ROOT, "uemda", "gast", "alignment.pyc")):
+        return _BUILT_ROOT
+    return _SRC_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "uemda", "gast"))
+    return (os.path.isdir(os.path.join(REFERENCE_ROOT, "uemda", "gast"))
+            and any(os.path.exists(os.path.join(REFERENCE_ROOT, "uemda", "gast", "alignment" + ext)) for ext in (".py", ".pyc")))
+
+
+def reference_kind():
+    """'source' (the tree under /root/reference), 'built' (oracle/_ref bytecode of the same files) or None."""
+    if not reference_available():
+        return None
+    return "built" if REFERENCE_ROOT == _BUILT_ROOT else "source"
 
 
 def _scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
@@ -92,8 +113,25 @@ def _install_stubs():
     ds.__all__ = []
     sys.modules.setdefault("uemda.datasets", ds)
     if not torch.cuda.is_available():
+        force_cpu()
+
+
+_saved_cuda = {}
+
+
+def force_cpu():
+    """The reference moves its state with ``.cuda()`` (alignment.py:48-77, balance.py:25): make that the identity so its
+    functions run on the host cores (always the case in the build container; on the GPU box this is what makes the CPU
+    arm a CPU arm).  ``restore_cuda()`` undoes it."""
+    if not _saved_cuda:
+        _saved_cuda["tensor"], _saved_cuda["module"] = torch.Tensor.cuda, torch.nn.Module.cuda
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+def restore_cuda():
+    if _saved_cuda:
+        torch.Tensor.cuda, torch.nn.Module.cuda = _saved_cuda.pop("tensor"), _saved_cuda.pop("module")
 
 
 _loaded = {}

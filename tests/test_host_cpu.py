@@ -149,6 +149,14 @@ h_all, v_all = O.class_histogram(down, wl.c)
 assert torch.allclose(S, s_all, rtol=1e-5, atol=1e-5)
 assert torch.equal(N, n_all.reshape(-1).long())
 assert torch.equal(Hh[:-1], h_all) and int(Hh[-1]) == int(v_all)
+# ClassBalance over a sharded batch (balance.py:45-52 is batch-global): the frequency EMA fed by the all-reduced
+# histogram equals the un-sharded one; fed by the rank-local histogram it does not
+freq0 = torch.ones(wl.c) / wl.c
+want_freq, want_w = O.class_balance_step(freq0, down, wl.c)[:2]
+red = torch.cat([hist, valid.reshape(1).long()]).clone()
+dist.all_reduce(red, op=dist.ReduceOp.SUM)
+got_freq = (1.0 - 0.99) * (red[:-1].float() / (red[-1].float() + 1e-7)) + 0.99 * freq0
+assert torch.equal(got_freq, want_freq), (got_freq, want_freq)
 assert int(mx) == int(inp["sup"].max())
 # the three-phase form: one all_gather of [sums | counts | max id], folded in rank order on every rank
 packed = pack_local(s, n.reshape(-1).long(), inp["sup"][lo:hi].max().reshape(1))

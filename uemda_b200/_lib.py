@@ -72,6 +72,15 @@ SIGNATURES = {
     "uem_pack_local_f64": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "uem_pack_local_partials_f64": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "uem_fold_gathered_f64": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "uem_xchg_region_bytes": (_L, [_I, _I, _I, _I]),
+    "uem_xchg_send_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "uem_xchg_wait_maxid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "uem_xchg_fold_finalize_ema_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
+    "uem_xchg_status": (_I, [_P, _P, _P]),
+    "uem_peer_alloc": (_I, [_L, _P, _P]),
+    "uem_peer_open": (_I, [_P, _P]),
+    "uem_peer_close": (_I, [_P]),
+    "uem_peer_free": (_I, [_P]),
     "uem_uvem_loss_forward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "uem_uvem_loss_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
 }

@@ -1,0 +1,314 @@
+// Multi-GPU exchange of the per-step statistics as device-side peer stores over NVLink.
+//
+// What crosses the fabric per step and rank (reference lines the exchange reproduces for a batch sharded by image):
+//   * prototype partial sums (c,k) fp32 + counts (c) int64          alignment.py:347-353 (sums over the WHOLE batch)
+//   * class histogram (c) + valid count, int64                      balance.py:45-52 (batch-global label frequencies)
+//   * the rank-local max superpixel id, int64                       alignment.py:241 (batch-global "ignored" id)
+// ~48 KiB at c = 6, k = 2048.  Instead of a host-issued NCCL all-gather between two CUDA graphs, every rank STORES its
+// vector straight into a slot of every peer's symmetric region (peer-mapped device memory: torch symmetric memory or
+// cudaIpc handles) followed by a release flag, and the consumer side acquires the flags in a kernel of its own graph:
+//
+//   uem_xchg_send_f32            grid (chunks, world): CTA (ch, p) folds chunk ch of this rank's per-image partials in
+//                                image order and stores it into peer p's slot [slot][rank]; the last chunk CTA of peer p
+//                                publishes data_flag[slot][rank] = sequence number on p (st.release.sys).
+//   uem_xchg_wait_maxid          one warp: lane r acquires data_flag[slot][r], then the batch-global max id = max over
+//                                the ranks' ids (needed by the refine kernel, so this sits at the head of phase B).
+//   uem_xchg_fold_finalize_ema   folds the world slots in RANK ORDER (identical fp32 additions on every rank -> the
+//                                replicated prototype bank stays bit-identical), local mean, keep-old rule, EMA; the last
+//                                CTA acknowledges the slot to every peer (ack_flag[slot][rank] on the peer), which is
+//                                what a sender waits for before it overwrites that slot `depth` steps later.
+// No kernel waits for a kernel that is queued behind it on its own GPU: a send of step s waits for the acks of step
+// s - depth, a wait of step s for the sends of step s -- both are upstream in every rank's stream order, so the scheme
+// cannot deadlock however the ranks drift.  Every spin is bounded (2 s of %globaltimer): on a timeout status bit 8 is set
+// in the region header and the kernel carries on, so a lost peer shows up as an error code, not as a hung GPU.
+//
+// Region layout (same on every rank; all offsets from the region base):
+//   [0, 1024)            header, local only: seq_send[4], seq_recv[4], arrive[4][16], arrive_all[4], fold_arrive[4], status
+//   [1024, 1280)         data_flag[4][16] u32      written by peers
+//   [1280, 1536)         ack_flag[4][16] u32       written by peers
+//   [2048, ...)          slots[depth][world][slot_bytes]
+// slot: [c*k sums f32 | pad to 16 B][c counts i64][c+1 hist i64][max id i64]
+#include "uem_common.cuh"
+#include <limits.h>
+#include <stddef.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr int kMaxDepth = 4;
+constexpr int kSendChunks = 6;
+constexpr int kOffFlags = 1024, kOffAcks = 1280, kOffSlots = 2048;
+constexpr unsigned long long kSpinLimitNs = 2000000000ull;
+
+struct XHeader {
+    unsigned seq_send[kMaxDepth];
+    unsigned seq_recv[kMaxDepth];
+    unsigned arrive[kMaxDepth][kMaxWorld];
+    unsigned arrive_all[kMaxDepth];
+    unsigned fold_arrive[kMaxDepth];
+    int status;
+};
+static_assert(sizeof(XHeader) <= kOffFlags, "header overflows its page");
+
+struct Peers {
+    char* base[kMaxWorld];
+};
+
+__host__ __device__ inline int64_t sums_bytes(int c, int k) { return (((int64_t)c * k * 4) + 15) & ~(int64_t)15; }
+__host__ __device__ inline int64_t slot_bytes(int c, int k) { return (sums_bytes(c, k) + (int64_t)(2 * c + 2) * 8 + 127) & ~(int64_t)127; }
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded spin until *flag >= want; returns false on timeout
+__device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned want) {
+    if ((int)(ld_acquire_sys(flag) - want) >= 0) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(flag) - want) < 0) {
+        __nanosleep(64);
+        if (globaltimer_ns() - t0 > kSpinLimitNs) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial, int b,
+                                                        int c, int k, const int64_t* __restrict__ max_id,
+                                                        const int64_t* __restrict__ hist, const Peers peers, int rank, int world,
+                                                        int slot) {
+    const int ch = blockIdx.x, p = blockIdx.y;
+    char* const mine = peers.base[rank];
+    XHeader* hdr = reinterpret_cast<XHeader*>(mine);
+    __shared__ unsigned s_my;
+    if (threadIdx.x == 0) {
+        const unsigned my = *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) + 1u;
+        // peer p must have folded the previous contents of this slot (its ack lands in MY region)
+        const unsigned* ack = reinterpret_cast<const unsigned*>(mine + kOffAcks) + slot * kMaxWorld + p;
+        if (!spin_until(ack, my - 1u)) atomicOr(&hdr->status, 8);
+        s_my = my;
+    }
+    __syncthreads();
+    const unsigned my = s_my;
+    const int ck = c * k;
+    const int64_t sb = slot_bytes(c, k);
+    char* dst = peers.base[p] + kOffSlots + ((int64_t)slot * world + rank) * sb;
+    // chunk ch of the sums, in units of 4 floats; per-image partials folded in image order (the same fp32 additions as
+    // proto_fold_kernel / proto_fold_finalize_kernel: a one-rank exchange reproduces the single-GPU step bit for bit)
+    const int nvec = (ck + 3) / 4;
+    const int v0 = (int)((int64_t)nvec * ch / gridDim.x), v1 = (int)((int64_t)nvec * (ch + 1) / gridDim.x);
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((ck & 3) == 0) {
+            for (int bi = 0; bi < b; ++bi) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)bi * ck) + v);
+                s[0] += q.x; s[1] += q.y; s[2] += q.z; s[3] += q.w;
+            }
+        } else {
+            for (int bi = 0; bi < b; ++bi)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (4 * v + u < ck) s[u] += partial[(int64_t)bi * ck + 4 * v + u];
+        }
+        *reinterpret_cast<float4*>(dst + (int64_t)v * 16) = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    if (ch == 0 && threadIdx.x < 2 * c + 2) {
+        int64_t* tail = reinterpret_cast<int64_t*>(dst + sums_bytes(c, k));
+        const int i = threadIdx.x;
+        int64_t v;
+        if (i < c) {
+            v = 0;
+            for (int bi = 0; bi < b; ++bi) v += cnt_partial[bi * c + i];
+        } else if (i < 2 * c + 1) {
+            v = hist ? hist[i - c] : 0;
+        } else {
+            v = max_id ? max_id[0] : -1;
+        }
+        tail[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(&hdr->arrive[slot][p], 1u);
+        if (old == gridDim.x - 1) {   // every chunk of peer p's copy is on its way: publish
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[p] + kOffFlags) + slot * kMaxWorld + rank, my);
+            hdr->arrive[slot][p] = 0u;
+            const unsigned old2 = atomicAdd(&hdr->arrive_all[slot], 1u);
+            if (old2 == (unsigned)world - 1u) {   // the last CTA of the launch: nobody reads seq_send any more
+                hdr->arrive_all[slot] = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) = my;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) xchg_wait_maxid_kernel(char* __restrict__ region, int world, int slot, int c, int k,
+                                                             int64_t* __restrict__ max_id_out) {
+    XHeader* hdr = reinterpret_cast<XHeader*>(region);
+    const unsigned want = *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) + 1u;
+    const int r = threadIdx.x;
+    long long id = LLONG_MIN;
+    if (r < world) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(region + kOffFlags) + slot * kMaxWorld + r;
+        if (!spin_until(flag, want)) atomicOr(&hdr->status, 8);
+        const int64_t sb = slot_bytes(c, k);
+        const char* src = region + kOffSlots + ((int64_t)slot * world + r) * sb + sums_bytes(c, k);
+        id = *reinterpret_cast<const volatile long long*>(src + (int64_t)(2 * c + 1) * 8);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, id, o);
+        id = other > id ? other : id;
+    }
+    if (r == 0 && max_id_out) max_id_out[0] = id;
+}
+
+__global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers peers, int rank, int world, int slot, int c, int k,
+                                                                 const float* __restrict__ proto_old, float eps, float one_minus_decay,
+                                                                 float decay, float* __restrict__ proto_new, float* __restrict__ sums_out,
+                                                                 int64_t* __restrict__ counts_out, int64_t* __restrict__ hist_out) {
+    char* const region = peers.base[rank];
+    XHeader* hdr = reinterpret_cast<XHeader*>(region);
+    const unsigned want = *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) + 1u;
+    if (threadIdx.x < world) {   // uem_xchg_wait_maxid must have run before on this stream: verify, never spin here
+        const unsigned* flag = reinterpret_cast<const unsigned*>(region + kOffFlags) + slot * kMaxWorld + threadIdx.x;
+        if ((int)(ld_acquire_sys(flag) - want) < 0) atomicOr(&hdr->status, 16);
+    }
+    __syncthreads();
+    const int ck = c * k;
+    const int64_t sb = slot_bytes(c, k);
+    const char* slots = region + kOffSlots + (int64_t)slot * world * sb;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < ck) {
+        const int ci = i / k;
+        float s = *reinterpret_cast<const float*>(slots + (int64_t)i * 4);
+        int64_t n = *reinterpret_cast<const int64_t*>(slots + sums_bytes(c, k) + (int64_t)ci * 8);
+        for (int r = 1; r < world; ++r) {   // rank order: identical on every rank
+            s += *reinterpret_cast<const float*>(slots + r * sb + (int64_t)i * 4);
+            n += *reinterpret_cast<const int64_t*>(slots + r * sb + sums_bytes(c, k) + (int64_t)ci * 8);
+        }
+        if (sums_out) sums_out[i] = s;
+        if (proto_new) {
+            const float old = proto_old[i];
+            float local = s / ((float)n + eps);                 // alignment.py:348
+            if (n < 1) local = old;                             // :350
+            proto_new[i] = __fadd_rn(__fmul_rn(one_minus_decay, local), __fmul_rn(decay, old));   // :465
+        }
+    }
+    if (i < 2 * c + 1 && (counts_out || hist_out)) {
+        int64_t n = 0;
+        for (int r = 0; r < world; ++r) n += *reinterpret_cast<const int64_t*>(slots + r * sb + sums_bytes(c, k) + (int64_t)i * 8);
+        if (i < c) { if (counts_out) counts_out[i] = n; }
+        else if (hist_out) hist_out[i - c] = n;
+    }
+    // the last CTA acknowledges the slot to every peer and advances the local sequence number
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->fold_arrive[slot], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + kOffAcks) + slot * kMaxWorld + rank, want);
+        if (threadIdx.x == 0) {
+            hdr->fold_arrive[slot] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) = want;
+        }
+    }
+}
+
+int fill_peers(Peers* P, const void* const* peer_regions, int rank, int world, int depth, int slot, const char* who) {
+    UEM_REQUIRE(peer_regions && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "%s: bad rank/world (%d/%d, at most %d ranks)",
+                who, rank, world, kMaxWorld);
+    UEM_REQUIRE(depth >= 1 && depth <= kMaxDepth && slot >= 0 && slot < depth, "%s: bad slot/depth (%d/%d, depth at most %d)", who, slot,
+                depth, kMaxDepth);
+    for (int r = 0; r < kMaxWorld; ++r) P->base[r] = r < world ? (char*)peer_regions[r] : nullptr;
+    for (int r = 0; r < world; ++r) UEM_REQUIRE(P->base[r], "%s: peer region %d is NULL", who, r);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t uem_xchg_region_bytes(int world, int depth, int c, int k) {
+    if (world < 1 || world > kMaxWorld || depth < 1 || depth > kMaxDepth || c < 1 || k < 1) return -1;
+    return kOffSlots + (int64_t)depth * world * slot_bytes(c, k);
+}
+
+extern "C" int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
+                                 const void* const* peer_regions, int rank, int world, int depth, int slot, void* stream) {
+    UEM_REQUIRE(partials_ws && b > 0 && c > 0 && c <= UEM_MAX_C && k > 0, "uem_xchg_send_f32: bad arguments");
+    Peers P;
+    if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_send_f32")) return rc;
+    const float* partial = (const float*)partials_ws;
+    const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
+    xchg_send_kernel<<<dim3(kSendChunks, world), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, max_id, hist, P, rank, world,
+                                                                                slot);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_xchg_wait_maxid(void* region, int world, int depth, int slot, int c, int k, int64_t* max_id_out, void* stream) {
+    UEM_REQUIRE(region && world >= 1 && world <= kMaxWorld && depth >= 1 && depth <= kMaxDepth && slot >= 0 && slot < depth && c > 0 && k > 0,
+                "uem_xchg_wait_maxid: bad arguments");
+    xchg_wait_maxid_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((char*)region, world, slot, c, k, max_id_out);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, int rank, int world, int depth, int slot, int c, int k,
+                                              const float* proto_old, float eps, float one_minus_decay, float decay, float* proto_new,
+                                              float* sums_out, int64_t* counts_out, int64_t* hist_out, void* stream) {
+    UEM_REQUIRE(c > 0 && c <= UEM_MAX_C && k > 0 && (!proto_new || proto_old), "uem_xchg_fold_finalize_ema_f32: bad arguments");
+    Peers P;
+    if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_fold_finalize_ema_f32")) return rc;
+    xchg_fold_finalize_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, rank, world, slot, c, k, proto_old, eps, one_minus_decay, decay, proto_new, sums_out, counts_out, hist_out);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_xchg_status(const void* region, int* status_out, void* stream) {
+    UEM_REQUIRE(region && status_out, "uem_xchg_status: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    UEM_CUDA(cudaMemcpyAsync(status_out, (const char*)region + offsetof(XHeader, status), sizeof(int), cudaMemcpyDeviceToHost, st));
+    UEM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- cudaIpc plumbing for the symmetric region (used when torch's symmetric memory is unavailable) ----------------------
+extern "C" int uem_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+    UEM_REQUIRE(bytes > 0 && ptr && handle64, "uem_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    UEM_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    UEM_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+    UEM_CUDA(cudaDeviceSynchronize());
+    UEM_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, *ptr));
+    return 0;
+}
+extern "C" int uem_peer_open(const void* handle64, void** ptr) {
+    UEM_REQUIRE(handle64 && ptr, "uem_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    UEM_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int uem_peer_close(void* ptr) {
+    if (ptr) UEM_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+extern "C" int uem_peer_free(void* ptr) {
+    if (ptr) UEM_CUDA(cudaFree(ptr));
+    return 0;
+}

@@ -5,7 +5,12 @@
 // product (:438-440, 403 MB at config 2).  Here the NCHW map is read exactly once, in place:
 // threads run along the pixel dimension (128-bit loads, 128 B per class-of-8-lanes), the k dimension is
 // split over 32 slices per CTA, and each thread keeps 2+m running sums per pixel:
-//   S1 = sum g, S2 = sum g^2, Cj = sum g * pc_j      with g = f - pivot (pivot = f at channel 0)
+//   S1 = sum g, S2 = sum g^2, Cj = sum g * pc_j      with g = f - pivot
+// The pivot is the pixel's mean over 8 channels spread over k (channels i*(k/8)): an estimate of the per-pixel mean
+// that is within sigma/sqrt(8) of it, so the one-pass variance S2 - S1^2/k loses ~1.1x (a 4-sigma channel-0 value used
+// as the pivot would lose 17x) and |g| stays at the scale of the centred feature.  Measured against fp64 at k = 2048 on
+// the near-prototype set (feat = proto + 0.05 noise, dist ~ 5e-4): 2.4e-7 absolute on dist, the reference's own fp32
+// centre-then-dot form is at 1.7e-7 (tests/test_gpu_parity.py::test_pearson_benchmarked_shapes).
 // where pc_j is the centred prototype (sum_k pc_j ~ 0, so centring f is unnecessary for the covariance;
 // the residual mean(g)*sum(pc_j) is subtracted anyway).  HBM-bound on feat: 4k B per feature pixel.
 #include "uem_common.cuh"
@@ -97,8 +102,21 @@ __global__ void __launch_bounds__(kPearsonThreads, 4) pearson_nchw_kernel(const 
         for (int i = 0; i < VEC; ++i) acc[a][i] = 0.f;
 
     if (active) {
-        PixVec<VEC> piv;
-        piv.load(f);  // channel 0 of these pixels: the shift that keeps the one-pass variance stable
+        PixVec<VEC> piv;   // mean over 8 spread channels: the shift that keeps the one-pass variance stable
+        {
+            const int kstep = k >> 3;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) piv.v[i] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                PixVec<VEC> q;
+                q.load(f + (int64_t)(u * kstep) * hw);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) piv.v[i] += q.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) piv.v[i] *= 0.125f;
+        }
         auto consume = [&](const PixVec<VEC>& v, int kk) {
             float pcv[kPcStride];
             const float4 a = __ldg(reinterpret_cast<const float4*>(pc + (int64_t)kk * kPcStride));
@@ -244,10 +262,18 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
         const int px = px0 + lane * 4;
         const bool inb = px < hw;  // hw % 4 == 0
         float2 piv01 = make_float2(0.f, 0.f), piv23 = make_float2(0.f, 0.f);
-        if (inb) {  // channel 0 of these pixels: the shift that keeps the one-pass variance stable (same for every k split)
-            const float4 pv = ldg_f4(feat + (int64_t)bi * k * hw + px);
-            piv01 = make_float2(-pv.x, -pv.y);
-            piv23 = make_float2(-pv.z, -pv.w);
+        if (inb) {  // mean over 8 spread channels of these pixels: the shift that keeps the one-pass variance stable
+            // (same channels, same order for every k split: the splits' partial sums share one pivot bit for bit)
+            const float* f0 = feat + (int64_t)bi * k * hw + px;
+            const int64_t kstep = (int64_t)(k >> 3) * hw;
+            float4 q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = ldg_f4(f0 + u * kstep);
+            float4 pv = q[0];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) { pv.x += q[u].x; pv.y += q[u].y; pv.z += q[u].z; pv.w += q[u].w; }
+            piv01 = make_float2(-0.125f * pv.x, -0.125f * pv.y);
+            piv23 = make_float2(-0.125f * pv.z, -0.125f * pv.w);
         }
         float2 acc[NA][2];
 #pragma unroll
@@ -352,7 +378,10 @@ __global__ void __launch_bounds__(256) pearson_rows_kernel(const float* __restri
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
     const float* f = f1 + row * k;
-    const float piv = f[0];
+    float piv = 0.f;   // mean over 8 spread elements (see the header comment)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) piv += f[u * (k >> 3)];
+    piv *= 0.125f;
     for (int j0 = 0; j0 < m; j0 += 8) {
         const int mj = min(8, m - j0);
         float S1 = 0.f, S2 = 0.f, Cj[8];

@@ -32,6 +32,14 @@ class ClassBalance(nn.Module):
         self.temperature = temperature
         self.eps = 1e-7
         self.freq = torch.ones([class_num], device="cuda").float() / class_num
+        self._dist = None   # set by shard(): label histograms are summed over the ranks of a batch-sharded job
+        self._group = None
+
+    def shard(self, dist=None, group=None):
+        """Batch sharded over ranks (one process per GPU): the per-batch label histogram of balance.py:45-52 is over the
+        WHOLE batch, so the local histograms are all-reduced (c+1 int64 values) before the frequency EMA moves."""
+        self._dist, self._group = dist, group
+        return self
 
     def get_class_weight_4pixel(self, label):
         self.ema_update(label)  # the EMA moves first, then the lookup uses the new table (balance.py:28)
@@ -46,6 +54,8 @@ class ClassBalance(nn.Module):
 
     def _local_freq(self, label):
         hist = ops.class_hist(label, self.class_num, self.ignore_label)  # (c+1,) int64, last = #valid
+        if self._dist is not None:
+            self._dist.all_reduce(hist, op=self._dist.ReduceOp.SUM, group=self._group)
         return hist[:-1].float() / (hist[-1].float() + self.eps)
 
     @staticmethod

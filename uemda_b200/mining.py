@@ -220,13 +220,62 @@ class ShardedMiner:
       * three-phase, for CUDA-graph replay with the collective kept OUTSIDE the captured regions:
         ``local_stats`` (capturable) -> ``exchange`` (one all_gather of <= 100 KB, eager) -> ``apply`` (capturable)."""
 
-    def __init__(self, aligner, group=None):
+    def __init__(self, aligner, group=None, exchange="nccl", depth=3):
+        """exchange: 'nccl' (host-issued collectives only), 'peer' (device-side peer stores, uemda_b200/exchange.py; raises
+        if the regions cannot be mapped) or 'auto' (peer when it can be set up, else nccl).  depth: exchange slots."""
         import torch.distributed as dist
         self.dist = dist
         self.aligner = aligner
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.peer = None
+        if exchange in ("peer", "auto") and self.world > 1:
+            from .exchange import ExchangeError, PeerExchange
+            try:
+                self.peer = PeerExchange.create(aligner.class_num, aligner.prototypes.shape[1], depth=depth, group=group,
+                                                device=aligner.prototypes.device)
+            except ExchangeError:
+                if exchange == "peer":
+                    raise
+
+    # ---- device-side form (one or two CUDA graphs per step, no host-issued collective): send -> receive_id -> apply_peer
+    def send_stats(self, partials, local_max_id, slot, hist=None):
+        """Capturable.  partials: ops.proto_accumulate(feat_s, down, ..., fold=False); local_max_id: what region_phase
+        returned; hist: optional (c+1,) class histogram of this rank's labels.  Stores this rank's vector into slot
+        ``slot`` of every rank."""
+        self.peer.send(partials, local_max_id, slot, hist=hist)
+
+    def receive_id(self, slot, out=None):
+        """Capturable.  Blocks the stream until every rank's vector has arrived -> batch-global ignored id (alignment.py:241)."""
+        return self.peer.wait_max_id(slot, out=out)
+
+    def apply_peer(self, slot, in_place=True, want_hist=False):
+        """Capturable, after receive_id on the same stream and after the last reader of the old prototype bank has been
+        enqueued: rank-ordered fold + EMA of the prototype bank (alignment.py:347-353); returns the global class
+        histogram when asked (balance.py:45-52)."""
+        al = self.aligner
+        new, _, _, hist = self.peer.fold_finalize(slot, al.prototypes, eps=al.eps, decay=al.decay,
+                                                  out=al.prototypes if in_place else None, want_hist=want_hist)
+        al.prototypes = new
+        return hist
+
+    # ---- class histogram over the global batch (balance.py:45-52)
+    def class_hist(self, label_local, class_num=None, ignore_label=None):
+        """(c+1,) int64: per-class pixel counts and the valid count over the GLOBAL batch: local histogram ->
+        all_reduce(SUM).  ClassBalance._local_freq is batch-global in the un-sharded reference."""
+        al = self.aligner
+        hist = ops.class_hist(label_local, al.class_num if class_num is None else class_num,
+                              al.ignore_label if ignore_label is None else ignore_label)
+        if self.world > 1:
+            self.dist.all_reduce(hist, op=self.dist.ReduceOp.SUM, group=self.group)
+        return hist
+
+    def shard_class_balancer(self, balancer):
+        """Makes a ClassBalance (uemda_b200.gast.balance) all-reduce its label histograms over this miner's group, so a
+        sharded UVEMLoss(class_balancer=...) sees the frequencies of the whole batch like the un-sharded reference."""
+        balancer.shard(self.dist if self.world > 1 else None, self.group)
+        return balancer
 
     # ---- three-phase form
     def local_stats(self, sup_local, feat_s_local, label_s_local, out=None, local_max_id=None):

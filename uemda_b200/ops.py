@@ -318,9 +318,10 @@ def proto_weight_4pixel(simi, hard, ignore_label=-1, eps=1e-7):
 
 
 # --------------------------------------------------------------------------------------------- a10-a12
-def proto_accumulate(feat, label_down, class_num, ignore_label=-1, fold=True):
+def proto_accumulate(feat, label_down, class_num, ignore_label=-1, fold=True, ws=None):
     """Masked per-class feature sums (c,k) fp32 and counts (c,) int64 (alignment.py:341-348).
-    fold=False: returns the opaque per-image partials (for proto_fold_finalize) instead."""
+    fold=False: returns the opaque per-image partials (for proto_fold_finalize) instead.
+    ws: optional preallocated scratch (``proto_accumulate_ws``): a static buffer when the partials cross CUDA graphs."""
     L.require_cuda(feat, label_down)
     feat = L.f32c(feat.detach())
     label = L.i64c(label_down.detach())
@@ -329,12 +330,20 @@ def proto_accumulate(feat, label_down, class_num, ignore_label=-1, fold=True):
     lib = L.bind(feat)
     sums = torch.empty((class_num, k), dtype=torch.float32, device=feat.device) if fold else None
     counts = torch.empty((class_num,), dtype=torch.int64, device=feat.device) if fold else None
-    ws = L.workspace(lib.uem_proto_accum_ws_bytes(b, class_num, k), feat)
+    need = lib.uem_proto_accum_ws_bytes(b, class_num, k)
+    if ws is None:
+        ws = L.workspace(need, feat)
+    assert ws.numel() >= need and ws.device == feat.device
     L.check(lib.uem_proto_accum_nchw_f32(L.ptr(feat), b, k, h * w, L.ptr(label), class_num, int(ignore_label), L.ptr(sums),
                                          L.ptr(counts), L.ptr(ws), L.stream_of(feat)))
     if not fold:
         return ws, (b, class_num, k)
     return sums, counts
+
+
+def proto_accumulate_ws(b, class_num, k, device):
+    """Scratch of proto_accumulate for a (b, k, h, w) feature map (holds the per-image partial sums and counts)."""
+    return torch.empty(max(int(L.load().uem_proto_accum_ws_bytes(b, class_num, k)), 16), dtype=torch.uint8, device=device)
 
 
 def proto_fold_finalize(partials, proto_old, eps=1e-7, decay=0.999, out=None):
