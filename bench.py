@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of a CPU leg")
+    ap.add_argument("--refine-form", type=int, default=None, help="development: 0 / 1 = form of the fused refine kernel")
     return ap.parse_args()
 
 
@@ -278,13 +279,14 @@ def make_sets(wl, nsets, dev, rank, world, gen_images=None):
 
 
 class Pipeline:
-    """The device-resident step as ONE CUDA graph per step.
+    """The device-resident step as ONE CUDA graph per step, software-pipelined across steps.
 
-    Phase A (source statistics + the region half of the target chain [+ the exchange send]) reads neither the prototype
-    bank nor anything phase B writes, so graph j holds phase B of buffer set j and, as a parallel branch, phase A of set
-    j+1: a software pipeline across steps with one graph launch per step (same results as running the steps back to back).
-    N > 1 with the peer exchange: A ends with uem_xchg_send_f32 (peer stores), B starts with uem_xchg_wait_maxid and ends
-    with the rank-ordered fold + EMA -- no host-issued collective anywhere in the loop."""
+    Only refine -> selection of a step depend on each other and on everything else; the source statistics and the region
+    phase of the NEXT batch read neither the prototype bank nor anything this step writes, and the Pearson pass of the next
+    batch only needs this step's EMA, whose own inputs were ready one step ago.  Graph j therefore holds four parallel
+    branches (see step_body), and the critical path of a step is refine + selection instead of the sum of all kernels.
+    N > 1 with the peer exchange: uem_xchg_wait_maxid heads the graph, uem_xchg_send_f32 (peer stores) ends the region /
+    source branches, the rank-ordered fold + EMA is the EMA -- no host-issued collective anywhere in the loop."""
 
     def __init__(self, wl, sets, capacity, protos, dev, miner=None, use_graph=True):
         from uemda_b200 import _lib, mining, ops
@@ -311,60 +313,96 @@ class Pipeline:
         self.outs = [None] * self.n
         # the target chain is the critical path: high-priority stream; phase A fills the gaps from low-priority streams
         self.main = torch.cuda.Stream(device=dev, priority=-1)
-        self.ahead = torch.cuda.Stream(device=dev, priority=0)
-        self.side = torch.cuda.Stream(device=dev, priority=0)
+        self.br_proto = torch.cuda.Stream(device=dev, priority=-1)   # the next step's refine kernel waits for this one
+        self.br_region = torch.cuda.Stream(device=dev, priority=0)
+        self.br_source = torch.cuda.Stream(device=dev, priority=0)
         self.use_graph = use_graph
         self.graphs = None
         self.peer = miner.peer if miner is not None else None
 
-    # ---- the two phases
-    def phase_a(self, j):
+    # ---- the parts of a step
+    def source_part(self, j):
+        """DownscaleLabel -> masked prototype sums of source batch j (alignment.py:86-90, :341-348) into static scratch"""
         s = self.sets[j]
-        cur = torch.cuda.current_stream(self.dev)
-        self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):   # source chain: DownscaleLabel -> masked prototype sums
-            down = self.al.downscale_gt(s["label_s"])
-            self.partials[j] = self.ops.proto_accumulate(s["feat_s"], down, self.wl.c, -1, fold=False, ws=self.partial_ws[j])
+        down = self.al.downscale_gt(s["label_s"])
+        self.partials[j] = self.ops.proto_accumulate(s["feat_s"], down, self.wl.c, -1, fold=False, ws=self.partial_ws[j])
+
+    def region_part(self, j):
+        """region maxima of target batch j -> superpixel-view weights + the rank-local max id (alignment.py:238-253)"""
+        s = self.sets[j]
         self.local_ids[j] = self.mining.region_phase(s["soft"], s["sup"], TEMP, self.R, self.ws[j], self.wl.h, self.wl.w, self.wl.k)
-        cur.wait_stream(self.side)
+
+    def send_part(self, j):
         if self.peer is not None:
             self.miner.send_stats(self.partials[j], self.local_ids[j], j % self.peer.depth)
 
-    def phase_b(self, j):
-        s = self.sets[j]
-        if self.peer is not None:
-            ignored = self.miner.receive_id(j % self.peer.depth, out=self.ignored[j])
-        else:
-            ignored = self.local_ids[j]   # one rank: the local max id is the global one
-        out = self.mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=self.proto_state, pred1=s["pred1"],
-                                        pred2=s["pred2"], sup=s["sup"], num_regions=self.R, ignored_id=ignored, eps=self.al.eps,
-                                        select=(CUTOFF[0], CUTOFF[1], -1), ws=self.ws[j], uvem=UVEM, regions_ready=True)
+    def ema_part(self, j):
+        """prototype EMA of step j (alignment.py:347-353): its last reader (the Pearson pass of step j) ran one step earlier"""
         if self.peer is not None:
             self.miner.apply_peer(j % self.peer.depth, in_place=True)
         else:
             self.ops.proto_fold_finalize(self.partials[j], self.proto_state, eps=self.al.eps, decay=DECAY, out=self.proto_state)
+
+    def proto_part(self, j):
+        """1/Pearson distance of target batch j against the CURRENT bank (alignment.py:215-217) into ws[j]"""
+        s = self.sets[j]
+        self.mining.proto_phase(s["feat"], self.proto_state, s["soft"].shape, self.R, self.ws[j], eps=self.al.eps)
+
+    def id_part(self, j):
+        if self.peer is not None:
+            return self.miner.receive_id(j % self.peer.depth, out=self.ignored[j])
+        return self.local_ids[j]   # one rank: the local max id is the global one
+
+    def refine_part(self, j, ignored):
+        s = self.sets[j]
+        out = self.mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=self.proto_state, pred1=s["pred1"],
+                                        pred2=s["pred2"], sup=s["sup"], num_regions=self.R, ignored_id=ignored, eps=self.al.eps,
+                                        select=(CUTOFF[0], CUTOFF[1], -1), ws=self.ws[j], uvem=UVEM, regions_ready=True,
+                                        simi_ready=True)
         self.outs[j] = out
         return out
 
     def step_body(self, j, serial=False):
-        """phase B of set j with phase A of set j+1 as a parallel branch (fork / join on the current stream);
-        serial: one after the other on the current stream (kernel-level timing: the refine kernel runs alone)."""
+        """Step j = refine + selection of set j on the current stream, with everything that does not depend on them as
+        parallel branches (fork / join): [EMA of step j -> Pearson of set j+1], [region phase of set j+1], [source
+        statistics of set j+1], then the exchange send of set j+1.  Same results as running the steps back to back: the
+        Pearson pass of step j+1 reads the bank right after the EMA of step j, as it would there.
+        serial: one after the other on the current stream (kernel-level timing: the timed kernel runs alone)."""
         cur = torch.cuda.current_stream(self.dev)
+        jn = (j + 1) % self.n
         if serial:
-            self.phase_b(j)
-            self.phase_a((j + 1) % self.n)
+            self.refine_part(j, self.id_part(j))
+            self.ema_part(j)
+            self.proto_part(jn)
+            self.region_part(jn)
+            self.source_part(jn)
+            self.send_part(jn)
             return
-        self.ahead.wait_stream(cur)
-        with torch.cuda.stream(self.ahead):
-            self.phase_a((j + 1) % self.n)
-        self.phase_b(j)
-        cur.wait_stream(self.ahead)
+        self.br_region.wait_stream(cur)
+        self.br_source.wait_stream(cur)
+        ignored = self.id_part(j)          # N > 1: blocks this stream until every rank's statistics of step j are here
+        self.br_proto.wait_stream(cur)
+        with torch.cuda.stream(self.br_proto):
+            self.ema_part(j)
+            self.proto_part(jn)
+        with torch.cuda.stream(self.br_source):
+            self.source_part(jn)
+        with torch.cuda.stream(self.br_region):
+            self.region_part(jn)
+            self.br_region.wait_stream(self.br_source)
+            self.send_part(jn)
+        self.refine_part(j, ignored)
+        cur.wait_stream(self.br_proto)
+        cur.wait_stream(self.br_region)
 
     def prime(self):
         """phase A of set 0 (what the previous step would have done); the pipeline then stays in sequence: step i runs
         phase B of set i % n and phase A of set (i+1) % n, and with the peer exchange every send is matched by one fold"""
         with torch.cuda.stream(self.main):
-            self.phase_a(0)
+            self.proto_part(0)
+            self.region_part(0)
+            self.source_part(0)
+            self.send_part(0)
         self.main.synchronize()
         self.pos = 0
 
@@ -513,7 +551,7 @@ def time_resident(wl, dev, rank, world, args, steps, warmup, miner=None, gen_ima
     protos = inp["prototypes"].to(dev)
     if miner is not None:
         miner.aligner.prototypes = protos.clone()
-    mode = "one graph per step: phase B of set j || phase A of set j+1"
+    mode = "one graph per step: [refine -> select](j) || [EMA(j) -> pearson(j+1)] || region(j+1) || source stats(j+1)"
     if miner is not None and miner.peer is None:
         run, outs, graphed, nccl_launches = nccl_pipeline(args, wl, sets, capacity, miner, dev)
         pipe = None
@@ -576,6 +614,8 @@ def main():
     from uemda_b200.gast.alignment import Aligner, DownscaleLabel
     from uemda_b200.gast.pseudo_generation import pseudo_selection
     lib = _lib.load()
+    if args.refine_form is not None:
+        _lib.check(lib.uem_set_option(b"refine_form", args.refine_form))
     config.strict_asserts = False
 
     inp, sets, capacity = make_sets(wl, args.sets, dev, rank, world)

@@ -39,6 +39,7 @@ extern "C" {
 #define UEM_VIEW_PRED 2
 #define UEM_VIEW_SUP 4
 #define UEM_VIEW_REGIONS_READY 8 /* uem_mine_refine_select_f32 only: uem_mine_region_phase_f32 already ran on this ws */
+#define UEM_VIEW_SIMI_READY 16   /* uem_mine_refine_select_f32 only: uem_mine_proto_phase_f32 already ran on this ws */
 
 /* region reduce ops (torch_scatter.scatter reduce=..., alignment.py:187,245) */
 #define UEM_REDUCE_SUM 0
@@ -104,6 +105,9 @@ UEM_API int uem_pseudo_select_f32(const float* mask, const float* cmax, int b, i
  * uem_class_stats_decode_f32: table -> cmax (b*c) and image_min (b) as plain floats (NaN if the bad flag is set),
  * for the reference's range assert (pseudo_generation.py:71). */
 UEM_API int64_t uem_class_stats_bytes(int b, int c);
+/* development switches (A/B runs, tests): "refine_form" = 0 (pixel-pair packed column walk) | 1 (class-pair packing) |
+ * -1 (the library default); the two forms of the fused label_refine kernel agree bit for bit. */
+UEM_API int uem_set_option(const char* name, int value);
 UEM_API int uem_select_entropy_stats_f32(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw,
                                  float cutoff_top, float cutoff_low, int64_t ignore_label, int64_t* out,
                                  const float* uvem_host, float* entropy, float* weight, void* stream);
@@ -186,6 +190,12 @@ UEM_API int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, int 
 UEM_API int64_t uem_mine_ws_maxid_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R);
 UEM_API int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
                               int w, int k, float temp, void* ws, void* stream);
+/* The prototype half on its own: 1/Pearson distance of feat (b,k,h,w) to protos (c,k) (alignment.py:215-217) into the
+ * similarity slot of ws.  It only depends on the prototype bank, so in a pipelined loop it runs as soon as the EMA of the
+ * previous step is done, next to that step's refine / selection kernels; uem_mine_refine_select_f32(views |
+ * UEM_VIEW_SIMI_READY, ...) then skips it (feat / protos may be NULL there). */
+UEM_API int uem_mine_proto_phase_f32(const float* feat, int k, const float* protos, int b, int c, int H, int W, int h, int w,
+                             int64_t R, float eps, void* ws, void* stream);
 UEM_API int uem_mine_refine_select_f32(int views, const float* feat, int k, const float* protos,
                                const float* pred1, const float* pred2, int h, int w, const int64_t* sup,
                                int64_t R, const int64_t* ignored_id, const float* soft, int b, int c, int H,

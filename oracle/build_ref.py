@@ -3,7 +3,7 @@
     python oracle/build_ref.py            (also run by __graft_entry__.build() when /root/reference is present)
 
 /root/reference does not exist on the GPU box, and the reference is pure Python, so "building" it means compiling the
-modules its mining path imports (found by import tracing under oracle/ref_shim.py) to sourceless ``.pyc`` files, from
+modules its mining path imports (found by import tracing under oracle/ref_shim.py) to bytecode files (``.refbin``), from
 the sources where they lie, into the git-ignored ``oracle/_ref/`` -- the same way a C reference would be compiled into a
 ``.so`` there.  No reference source is copied.  ``oracle/ref_shim.py`` then imports ``uemda.gast.{alignment,
 pseudo_generation, balance}`` and ``uemda.utils.tools`` from ``oracle/_ref`` when ``/root/reference`` is absent, which is
@@ -18,6 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("UEM_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
+BIN_EXT = ".refbin"
 
 # the modules uemda.gast.{alignment,pseudo_generation,balance} pull in under the shim (everything else is stubbed there)
 MODULES = [
@@ -41,7 +42,8 @@ def build(verbose=False):
         shutil.rmtree(OUT)
     for rel in MODULES:
         src = os.path.join(REFERENCE_ROOT, rel)
-        dst = os.path.join(OUT, rel + "c")   # sourceless import: <module>.pyc next to where the .py would be
+        dst = os.path.join(OUT, rel[:-3] + BIN_EXT)   # bytecode, loaded by ref_shim's importer (not named .pyc: snapshot
+        #                                               tools commonly drop *.pyc, and these files must travel to the GPU box)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile=rel, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -27,13 +27,14 @@ import types
 import torch
 
 _SRC_ROOT = os.environ.get("UEM_REFERENCE_ROOT", "/root/reference")
-_BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (sourceless .pyc)
+_BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (bytecode)
+_BIN_EXT = ".refbin"
 
 
 def _pick_root():
     if os.path.isdir(os.path.join(_SRC_ROOT, "uemda", "gast")):
         return _SRC_ROOT
-    if os.path.exists(os.path.join(_BUILT_ROOT, "uemda", "gast", "alignment.pyc")):
+    if os.path.exists(os.path.join(_BUILT_ROOT, "uemda", "gast", "alignment" + _BIN_EXT)):
         return _BUILT_ROOT
     return _SRC_ROOT
 
@@ -43,7 +44,7 @@ REFERENCE_ROOT = _pick_root()
 
 def reference_available():
     return (os.path.isdir(os.path.join(REFERENCE_ROOT, "uemda", "gast"))
-            and any(os.path.exists(os.path.join(REFERENCE_ROOT, "uemda", "gast", "alignment" + ext)) for ext in (".py", ".pyc")))
+            and any(os.path.exists(os.path.join(REFERENCE_ROOT, "uemda", "gast", "alignment" + ext)) for ext in (".py", _BIN_EXT)))
 
 
 def reference_kind():
@@ -134,6 +135,29 @@ def restore_cuda():
         torch.Tensor.cuda, torch.nn.Module.cuda = _saved_cuda.pop("tensor"), _saved_cuda.pop("module")
 
 
+class _BuiltFinder:
+    """meta-path finder for the byte-compiled reference modules under oracle/_ref (<module>.refbin / <pkg>/__init__.refbin)"""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname != "uemda" and not fullname.startswith("uemda."):
+            return None
+        base = os.path.join(self.root, *fullname.split("."))
+        pkg = os.path.join(base, "__init__" + _BIN_EXT)
+        if os.path.exists(pkg):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, pkg)
+            return importlib.util.spec_from_file_location(fullname, pkg, loader=loader, submodule_search_locations=[base])
+        mod = base + _BIN_EXT
+        if os.path.exists(mod):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, mod)
+            return importlib.util.spec_from_file_location(fullname, mod, loader=loader)
+        return None
+
+
 _loaded = {}
 
 
@@ -144,7 +168,10 @@ def load_reference():
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
+    if REFERENCE_ROOT == _BUILT_ROOT:
+        if not any(isinstance(f, _BuiltFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _BuiltFinder(_BUILT_ROOT))
+    elif REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     alignment = importlib.import_module("uemda.gast.alignment")
     pseudo = importlib.import_module("uemda.gast.pseudo_generation")

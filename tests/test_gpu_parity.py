@@ -1028,3 +1028,32 @@ def test_peer_exchange_reports_a_missing_fold(dev):
     bank = torch.zeros(3, 64, device=dev)
     xs[0].fold_finalize(0, bank, decay=0.9)
     assert xs[0].status() & 16
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 96, 256, 6, 16), (1, 7, 64, 192, 4, 12), (2, 5, 72, 200, 9, 25), (1, 8, 64, 256, 4, 16),
+                                   (1, 3, 40, 36, 20, 18), (8, 6, 512, 512, 32, 32)])
+def test_refine_kernel_forms_agree(dev, shape):
+    """The two forms of the column-walk refine kernel (round 1: class-pair packing; round 2: pixel-pair packing, FMNMX3,
+    D state in shared memory) keep every rounded operation in the same order: refined maps and class statistics are
+    bit-identical, so the faster form inherits every parity result of the first."""
+    from uemda_b200 import _lib, mining
+    b, c, H, W, h, w = shape
+    g = torch.Generator().manual_seed(H * 31 + W)
+    soft = torch.softmax(torch.randn(b, c, H, W, generator=g) * 3, dim=1).to(dev)
+    sup = torch.randint(0, 37, (b, 1, H, W), generator=g).to(dev)
+    k = 32
+    feat = torch.randn(b, k, h, w, generator=g).to(dev)
+    protos = torch.randn(c, k, generator=g).to(dev)
+    p1 = (torch.randn(b, c, h, w, generator=g) * 4).to(dev)
+    p2 = (torch.randn(b, c, h, w, generator=g) * 4).to(dev)
+    lib = _lib.load()
+    outs = []
+    try:
+        for form in (0, 1):
+            _lib.check(lib.uem_set_option(b"refine_form", form))
+            r, _ = mining.refine_select(7, soft, 2.0, feat=feat, prototypes=protos, pred1=p1, pred2=p2, sup=sup)
+            outs.append((r, r._uem_stats.stats.clone()))
+    finally:
+        lib.uem_set_option(b"refine_form", -1)
+    assert torch.equal(outs[0][0], outs[1][0]), "refined maps of the two kernel forms differ"
+    assert torch.equal(outs[0][1], outs[1][1]), "class statistics of the two kernel forms differ"

@@ -24,11 +24,13 @@ def main():
     ap.add_argument("--sets", type=int, default=3)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--only", default="")
+    ap.add_argument("--refine-form", type=int, default=0, help="0 = pixel-pair column walk (default), 1 = first form")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     _lib.load()
+    _lib.check(_lib.load().uem_set_option(b"refine_form", args.refine_form))
     config.strict_asserts = False
     inp = make_inputs(wl, seed=2333)
     keys = ("soft", "sup", "feat", "pred1", "pred2", "label_s", "feat_s")

@@ -26,6 +26,7 @@ SIGNATURES = {
     "uem_set_device": (_I, [_I]),
     "uem_kernel_launches": (_L, []),
     "uem_profile_refine_events": (_I, [_P, _P]),
+    "uem_set_option": (_I, [_c.c_char_p, _I]),
     "uem_softmax_conf_entropy_argmax_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "uem_entropy_uvem_weight_f32": (_I, [_P, _I, _I, _L, _F, _F, _F, _F, _F, _P, _P, _P]),
     "uem_uvem_weight_f32": (_I, [_P, _L, _F, _F, _F, _F, _F, _P, _P]),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "uem_mine_ws_stats_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_ws_maxid_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_region_phase_f32": (_I, [_P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "uem_mine_proto_phase_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _L, _F, _P, _P]),
     "uem_mine_refine_select_f32": (_I, [_I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F,
                                         _L, _P, _P, _P, _P, _P, _P, _P]),
     "uem_proto_weight_4pixel_f32": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _L, _F, _P, _P]),

@@ -23,6 +23,8 @@
 // (pseudo_generation.py:76) fall out as a (b, c+2) stats table raised with atomicMax.
 #include "uem_common.cuh"
 #include "uem_tma.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 int uem_region_table_f32(const float* src, int64_t sb, int64_t sn, int64_t sc, const int64_t* index, int b, int64_t N,
                          int c, int64_t R, int op, const int64_t* hot_ptr, int64_t hot_val, int skip_hot, unsigned* table,
@@ -383,8 +385,11 @@ __device__ __forceinline__ float4 ldg_f4_l1(const float4* p) {
 // VX = image columns per lane (1 or 2).  With VX = 2 a lane owns two adjacent columns: the per-row bookkeeping (loop,
 // prefetch cursor, row coordinate, store addressing) is shared by two pixels, their two dependent chains interleave,
 // shared-memory reads and global stores become 64-bit; the price is twice the column state (12*PC registers).
+#ifndef UEM_REFINE_COL_MINB_VX2
+#define UEM_REFINE_COL_MINB_VX2 3
+#endif
 template <int C, int NT, int NS, int VX>
-__global__ void __launch_bounds__(NT, ((VX == 2 ? 3 : UEM_REFINE_COL_MINB) * 128) / NT)
+__global__ void __launch_bounds__(NT, ((VX == 2 ? UEM_REFINE_COL_MINB_VX2 : UEM_REFINE_COL_MINB) * 128) / NT)
 refine_col_kernel(const RefineParams p, const int ncols_max) {
     constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32, WC = 32 * VX;
     constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
@@ -693,6 +698,387 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
     if (p.stats) flush(cur_b);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column-walk kernel, second form (round 2; the default): same decomposition as refine_col_kernel with two columns per
+// lane, but every per-pixel quantity is a float2 over the lane's TWO PIXELS (not over a pair of classes):
+//   * the packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2) then cover both pixels for every class, any class count
+//     (no padded class slot for odd C), including the final normalisation, the sums over classes and the NaN probe;
+//   * shared-memory reads of the soft planes (LDS.64) and the global stores (STG.64) are already in that layout: no
+//     re-packing moves between the class-pair and the pixel-pair form;
+//   * maxima over classes and the running class statistics use the 3-input FMNMX3 (max of C values in C/2 instructions,
+//     cmax/cmin of both pixels in one instruction per class);
+//   * the second half of the column state (D = B - A, 3C float2 per lane) lives in shared memory (DSM = 1): 128 registers
+//     -> 4 CTAs (16 warps) per SM instead of 3; it comes back as 3C conflict-free LDS.64 per row.
+// ~135 instructions per pixel in the row loop instead of ~192.  Every rounded operation is kept in the order of
+// refine_col_kernel (the class sums still add even and odd classes separately, the final sum is the same pairwise tree),
+// so the two kernels agree bit for bit (tests/test_gpu_parity.py::test_refine_kernel_forms_agree).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// per-pixel max over C class values held as (pixel 0, pixel 1) pairs
+template <int C> __device__ __forceinline__ float2 max_over_classes(const float2 (&z)[C]) {
+    float mx = z[0].x, my = z[0].y;
+    int i = 1;
+#pragma unroll
+    for (; i + 1 < C; i += 2) { mx = fmax3(mx, z[i].x, z[i + 1].x); my = fmax3(my, z[i].y, z[i + 1].y); }
+    if (i < C) { mx = fmaxf(mx, z[i].x); my = fmaxf(my, z[i].y); }
+    return make_float2(mx, my);
+}
+// e_c = 2^(z_c - max z) for both pixels; returns S = sum e_c added as (even classes) + (odd classes), the order of
+// exp2_shifted2 over class pairs
+template <int C> __device__ __forceinline__ float2 exp2_shifted_px(float2 (&z)[C]) {
+    const float2 mx = max_over_classes<C>(z);
+    const float2 nmx = make_float2(-mx.x, -mx.y);
+    float2 ev = make_float2(0.f, 0.f), od = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float2 d = UEM_FADD2(z[c], nmx);
+        z[c] = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+        if (c & 1) od = (c == 1) ? z[c] : UEM_FADD2(od, z[c]);
+        else ev = (c == 0) ? z[c] : UEM_FADD2(ev, z[c]);
+    }
+    return C > 1 ? UEM_FADD2(ev, od) : ev;
+}
+
+template <int C, int NT, int NS, int DSM, int MINB>
+__global__ void __launch_bounds__(NT, (MINB * 128) / NT)
+refine_col2_kernel(const RefineParams p, const int ncols_max) {
+    constexpr int CP = Lay<C>::CP, NW = NT / 32, WC = 64;
+    constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
+    constexpr uint32_t kPlane = (uint32_t)WC * 4u;               // bytes of one soft plane of a warp row
+    constexpr uint32_t kWarpStage = (uint32_t)WC * (4u * C + 8u);   // bytes of one row of a warp's WC columns
+    constexpr int CPP = WC / 4;                                  // 16-byte chunks per soft plane
+    constexpr int NCHUNK = CPP * C + WC / 2;                     // + the ids (2 per chunk)
+    constexpr int NCP = (NCHUNK + 31) / 32;                      // cp.async per lane and row
+    constexpr uint32_t kWarpD = DSM ? (uint32_t)(3 * C) * 32u * 8u : 0u;   // bytes of a warp's D state
+    extern __shared__ __align__(128) unsigned char smem_col[];
+    const int W = p.W, H = p.H, w = p.w, h = p.h;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t HW = (int64_t)H * W;
+    const int hw_low = h * w;
+    const int nstrips = (W + NT * 2 - 1) / (NT * 2);
+    // shared memory: [warp][stage][C planes x WC floats | WC ids]  [warp][3C][32 lanes] float2 D state  [warp][2][ncols_max][TS] taps
+    unsigned char* const wstage = smem_col + (size_t)wid * NS * kWarpStage;
+    const uint32_t dstate = smem_u32(smem_col + (size_t)NW * NS * kWarpStage + (size_t)wid * kWarpD) + (uint32_t)lane * 8u;
+    float* const taps = reinterpret_cast<float*>(smem_col + (size_t)NW * NS * kWarpStage + (size_t)NW * kWarpD) + (size_t)wid * 2 * ncols_max * TS;
+
+    const int64_t total = (int64_t)p.b * nstrips * H;
+    const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int n = (int)(U1 - U0);
+    if (n <= 0) return;
+    const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
+
+    // ---- prefetch side (as in refine_col_kernel): lane l copies 16-byte chunks l, l+32, ... of a warp row
+    const uint32_t wstage_u32 = smem_u32(wstage) + (uint32_t)lane * 16u;
+    const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * 8u;
+    int ibs = bs0, iy = y0, ibs_cur = -1;
+    const char* csrc[NCP];
+    uint32_t cstride[NCP];
+    bool cvalid[NCP];
+#pragma unroll
+    for (int q = 0; q < NCP; ++q) { csrc[q] = nullptr; cstride[q] = 0; cvalid[q] = false; }
+    auto prefetch = [&](int stage) {
+        if (ibs != ibs_cur) {
+            const int bi = ibs / nstrips, s = ibs - bi * nstrips;
+            const int xw = s * NT * 2 + wid * WC;
+#pragma unroll
+            for (int q = 0; q < NCP; ++q) {
+                const int k = lane + 32 * q;
+                if (k < CPP * C) {
+                    const int ci = k / CPP, x = xw + (k - ci * CPP) * 4;
+                    cvalid[q] = x < W;
+                    csrc[q] = reinterpret_cast<const char*>(p.soft + ((int64_t)bi * C + ci) * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
+                    cstride[q] = (uint32_t)W * 4u;
+                } else {
+                    const int x = xw + (k - CPP * C) * 2;
+                    cvalid[q] = (k < NCHUNK) && x < W;
+                    csrc[q] = reinterpret_cast<const char*>(p.sup + (int64_t)bi * HW + (int64_t)iy * W + (cvalid[q] ? x : 0));
+                    cstride[q] = (uint32_t)W * 8u;
+                }
+            }
+            ibs_cur = ibs;
+        }
+        const uint32_t d = wstage_u32 + (uint32_t)stage * kWarpStage;
+#pragma unroll
+        for (int q = 0; q < NCP; ++q) {
+            if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            csrc[q] += cstride[q];
+        }
+        if (++iy == H) { iy = 0; ++ibs; }
+    };
+#pragma unroll
+    for (int s = 0; s < NS - 1; ++s) {   // inputs only: safe before the dependency wait
+        if (s < n) prefetch(s);
+        cp_async_commit_group();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int64_t ignored_id = *p.ignored_id;
+    const uint32_t ign_lo = ((uint64_t)ignored_id >> 32) == 0 ? (uint32_t)ignored_id : 0xffffffffu;
+    const uint32_t Ru = (uint32_t)p.R;
+
+    // column state: A = pre-scaled lerp_x of low-res row i0, D = (row i1) - (row i0), as (pixel 0, pixel 1) pairs
+    float2 A[3][C];
+    float2 Dr[DSM ? 1 : 3][DSM ? 1 : C];
+    int cur_bs = -1, cur_i0 = -1, cur_b = -1;
+    int a0[2] = {0, 0}, a1[2] = {0, 0}, abase = 0, ncols = 1;
+    float l0x[2] = {0.f, 0.f}, l1x[2] = {0.f, 0.f};
+    bool active = false;
+    const float* ob = nullptr;
+    uint32_t x = 0;
+
+    float cmax[C];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) cmax[ci] = -INFINITY;
+    float cmin = INFINITY;
+    float2 nanacc = make_float2(0.f, 0.f);
+
+    auto flush = [&](int bi) {
+        float mn = warp_min(cmin);
+        const int anybad = __any_sync(0xffffffffu, (nanacc.x != nanacc.x) | (nanacc.y != nanacc.y));
+        float mine = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const float v = warp_max(cmax[ci]);
+            if (lane == ci) mine = v;
+            cmax[ci] = -INFINITY;
+        }
+        unsigned* srow = p.stats + (int64_t)bi * (C + 2);
+        if (lane < C) { if (mine > -INFINITY) atomicMax(srow + lane, f32_to_ordered(mine)); }
+        else if (lane == C) { if (mn < INFINITY) atomicMax(srow + C, f32_to_ordered(-mn)); }
+        else if (lane == C + 1) { if (anybad) atomicOr(srow + C + 1, 1u); }
+        cmin = INFINITY;
+        nanacc = make_float2(0.f, 0.f);
+    };
+
+    // region-weight gather, software-pipelined one row ahead: the ids of row it+1 are read as soon as that row has landed
+    // and its 2 x CP/4 table loads are issued before the arithmetic of row it, so their L2 latency (the table is only
+    // partly L1-resident: 35% hit rate measured) is covered by a whole row of work instead of stalling the multiply
+    float swn[2][C];
+    const float4* swb_n = nullptr;
+    auto gather = [&](int st_, bool act, const float4* tb) {
+        if (!act) return;
+        const uint32_t rd = rd_base + (uint32_t)st_ * kWarpStage;
+        int64_t rid[2];
+        asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(rid[0]), "=l"(rid[1]) : "r"(rd + (uint32_t)lane * 8u + (uint32_t)C * kPlane));
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            // multiplicative outside the ignored id; the ignored id and any id outside [0,R) go to the all-ones sentinel row R
+            const uint32_t lo = (uint32_t)rid[v], hi = (uint32_t)((uint64_t)rid[v] >> 32);
+            const bool in_region = (hi == 0u) & (lo < Ru) & (lo != ign_lo);
+            const uint32_t r = in_region ? lo : Ru;
+            const float* wp = reinterpret_cast<const float*>(tb + r * (uint32_t)(CP / 4));
+            // only the C live floats of the row: 128-bit loads, then one 64- or 32-bit load for a tail of 2 or 1
+#pragma unroll
+            for (int q = 0; q < C / 4; ++q) {
+                const float4 t = ldg_f4_l1(reinterpret_cast<const float4*>(wp) + q);
+                swn[v][4 * q] = t.x; swn[v][4 * q + 1] = t.y; swn[v][4 * q + 2] = t.z; swn[v][4 * q + 3] = t.w;
+            }
+            if constexpr (C % 4 == 3) {
+                const float4 t = ldg_f4_l1(reinterpret_cast<const float4*>(wp) + C / 4);
+                swn[v][C - 3] = t.x; swn[v][C - 2] = t.y; swn[v][C - 1] = t.z;
+            } else if constexpr (C % 4 == 2) {
+                asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0,%1}, [%2];" : "=f"(swn[v][C - 2]), "=f"(swn[v][C - 1]) : "l"(wp + (C & ~3)));
+            } else if constexpr (C % 4 == 1) {
+                asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(swn[v][C - 1]) : "l"(wp + (C & ~3)));
+            }
+        }
+    };
+    // geometry of an (image, strip) unit: is this lane inside the image, and which table does it gather from
+    auto lane_geom = [&](int bsu, bool& act, const float4*& tb) {
+        const int bi = bsu / nstrips, s = bsu - bi * nstrips;
+        act = (s * NT * 2 + wid * WC + lane * 2) < W;
+        tb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
+    };
+
+    int bs = bs0, y = y0;
+    int stage = 0, pstage = NS - 1;
+    {   // row 0's gather
+        cp_async_wait_group<NS - 2>();
+        __syncwarp();
+        bool act0;
+        lane_geom(bs0, act0, swb_n);
+        gather(0, act0, swb_n);
+    }
+    for (int it = 0; it < n; ++it) {
+        __syncwarp();
+        if (it + NS - 1 < n) prefetch(pstage);
+        cp_async_commit_group();
+        if (bs != cur_bs) {
+            const int bi = bs / nstrips, s = bs - bi * nstrips;
+            if (bi != cur_b) {
+                if (cur_b >= 0 && p.stats) flush(cur_b);
+                cur_b = bi;
+            }
+            const int xw = s * NT * 2 + wid * WC;
+            x = (uint32_t)(xw + lane * 2);
+            active = (int)x < W;     // W is even: the lane's two columns are both inside or both outside
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const Lerp lx = make_lerp(active ? (int)x + v : W - 1, w, p.sx);
+                a0[v] = lx.i0; a1[v] = lx.i1; l0x[v] = lx.l0; l1x[v] = lx.l1;
+            }
+            abase = make_lerp(min(xw, W - 1), w, p.sx).i0;
+            ncols = make_lerp(min(xw + WC - 1, W - 1), w, p.sx).i1 - abase + 1;
+            ob = p.out + (int64_t)bi * C * HW;
+            cur_bs = bs;
+            cur_i0 = -1;
+        }
+        const Lerp ly = make_lerp(y, h, p.sy);
+        if (ly.i0 != cur_i0) {
+            // new low-res row pair: the warp fetches the 2 x ncols x 3C values its 64 columns span (lane -> (map, class)),
+            // pre-scaled by log2 e [/temp]; every lane then interpolates its two columns horizontally, once
+            cur_i0 = ly.i0;
+            __syncwarp();
+            if (lane < 3 * C) {
+                const int m = lane / C, ci = lane - m * C;
+                const float* plane = p.maps[m] + ((int64_t)cur_b * C + ci) * hw_low + abase;
+                const float sc = p.map_scale[m];
+                float* dst = taps + m * CP + ci;
+                const float* r0 = plane + ly.i0 * w;
+                const float* r1 = plane + ly.i1 * w;
+                for (int j0 = 0; j0 < ncols; j0 += 4) {
+                    float u0[4], u1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = min(j0 + u, ncols - 1);
+                        u0[u] = __ldg(r0 + j);
+                        u1[u] = __ldg(r1 + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u < ncols) {
+                            dst[(j0 + u) * TS] = u0[u] * sc;
+                            dst[(ncols_max + j0 + u) * TS] = u1[u] * sc;
+                        }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                float ta[2][C], td[2][C];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const float* t00 = taps + (a0[v] - abase) * TS + m * CP;
+                    const float* t01 = taps + (a1[v] - abase) * TS + m * CP;
+                    float v00[CP], v01[CP], v10[CP], v11[CP];
+                    load_tap<C>(t00, v00);
+                    load_tap<C>(t01, v01);
+                    load_tap<C>(t00 + ncols_max * TS, v10);
+                    load_tap<C>(t01 + ncols_max * TS, v11);
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) {   // the rounded operations of refine_col_kernel, per component
+                        const float a = __fmaf_rn(l1x[v], v01[ci], __fmul_rn(l0x[v], v00[ci]));
+                        const float bq = __fmaf_rn(l1x[v], v11[ci], __fmul_rn(l0x[v], v10[ci]));
+                        ta[v][ci] = a;
+                        td[v][ci] = __fadd_rn(bq, -a);
+                    }
+                }
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    A[m][ci] = make_float2(ta[0][ci], ta[1][ci]);
+                    if constexpr (DSM) {
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(dstate + (uint32_t)(m * C + ci) * 256u), "f"(td[0][ci]), "f"(td[1][ci]) : "memory");
+                    } else {
+                        Dr[DSM ? 0 : m][DSM ? 0 : ci] = make_float2(td[0][ci], td[1][ci]);
+                    }
+                }
+            }
+        }
+        cp_async_wait_group<NS - 2>();   // rows it and it+1 have landed (this lane's chunks ...
+        __syncwarp();                    // ... and the other lanes': a row is read across lanes)
+        if (active) {
+            const uint32_t rd = rd_base + (uint32_t)stage * kWarpStage;   // this lane's two floats of plane 0
+            float2 sv[C];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci)
+                asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(sv[ci].x), "=f"(sv[ci].y) : "r"(rd + (uint32_t)ci * kPlane));
+            const float2 t2 = make_float2(ly.l1, ly.l1);
+            auto dstate_of = [&](int m, int ci) -> float2 {
+                if constexpr (DSM) {
+                    float2 d;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(d.x), "=f"(d.y) : "r"(dstate + (uint32_t)(m * C + ci) * 256u));
+                    return d;
+                } else {
+                    return Dr[DSM ? 0 : m][DSM ? 0 : ci];
+                }
+            };
+            float2 wgt[C];
+            {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
+                float2 z[C];
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) z[ci] = UEM_FFMA2(t2, dstate_of(0, ci), A[0][ci]);
+                const float2 S = exp2_shifted_px<C>(z);
+                const float2 rs = UEM_FFMA2(make_float2(-1e-7f, -1e-7f), S, make_float2(1.0f, 1.0f));
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) wgt[ci] = UEM_FMUL2(z[ci], rs);
+            }
+            {   // prediction view: mean of the two heads' softmax(logits/temp), / (max + 1e-7), scaled through by S1*S2
+                float2 z[C], z2[C];
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    z[ci] = UEM_FFMA2(t2, dstate_of(1, ci), A[1][ci]);
+                    z2[ci] = UEM_FFMA2(t2, dstate_of(2, ci), A[2][ci]);
+                }
+                const float2 S1 = exp2_shifted_px<C>(z);
+                const float2 S2 = exp2_shifted_px<C>(z2);
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) z[ci] = UEM_FFMA2(z[ci], S2, UEM_FMUL2(z2[ci], S1));
+                float2 mx = max_over_classes<C>(z);
+                mx = make_float2(fmaxf(mx.x, 0.f), fmaxf(mx.y, 0.f));
+                const float2 den = UEM_FFMA2(make_float2(2e-7f, 2e-7f), UEM_FMUL2(S1, S2), mx);
+                const float2 inv = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) wgt[ci] = UEM_FFMA2(z[ci], inv, wgt[ci]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) wgt[ci] = UEM_FMUL2(wgt[ci], make_float2(swn[0][ci], swn[1][ci]));   // gathered one row ago
+            // soft' = w*soft / (sum + 1e-7)   (alignment.py:291-292, :324-325); pairwise tree over class pairs
+            float2 o[C];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) o[ci] = UEM_FMUL2(wgt[ci], sv[ci]);
+            constexpr int PC = Lay<C>::PC;
+            float2 ps[PC];
+#pragma unroll
+            for (int j = 0; j < PC; ++j) ps[j] = (2 * j + 1 < C) ? UEM_FADD2(o[2 * j], o[2 * j + 1]) : o[2 * j];
+#pragma unroll
+            for (int st2 = 1; st2 < PC; st2 *= 2)
+#pragma unroll
+                for (int j = 0; j + st2 < PC; j += 2 * st2) ps[j] = UEM_FADD2(ps[j], ps[j + st2]);
+            const float2 ssum = ps[0];
+            const float2 sden = UEM_FADD2(ssum, make_float2(1e-7f, 1e-7f));
+            const float2 inv = make_float2(rcp_approx(sden.x), rcp_approx(sden.y));
+            nanacc = UEM_FFMA2(ssum, make_float2(0.f, 0.f), nanacc);   // s*0 accumulates to NaN iff a row sum was inf/NaN
+            const uint32_t idx = (uint32_t)y * (uint32_t)W + x;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                const float2 ov = UEM_FMUL2(o[ci], inv);
+                cmax[ci] = fmax3(cmax[ci], ov.x, ov.y);
+                cmin = fmin3(cmin, ov.x, ov.y);
+                *reinterpret_cast<float2*>(const_cast<float*>(ob + (int64_t)ci * HW) + idx) = ov;
+            }
+        }
+        if (it + 1 < n) {   // the next row's region weights: a whole row of work covers their latency
+            const int nst = (stage + 1 == NS) ? 0 : stage + 1;
+            bool actn = active;
+            if (y + 1 == H) lane_geom(bs + 1, actn, swb_n);   // the next row opens a new (image, strip)
+            gather(nst, actn, swb_n);
+        }
+        if (++y == H) { y = 0; ++bs; }
+        pstage = stage;
+        if (++stage == NS) stage = 0;
+    }
+    if (p.stats) flush(cur_b);
+}
+
 // superpixel-view weight of every (image, region): softmax(region_max/temp) / (max + 1e-7)  (alignment.py:252-253)
 // table: (b,R,C) ordered-u32 (encoded != 0) or fp32 region maxima -> sw (b,R+1,CP); row R (the sentinel the ignored
 // id and out-of-range ids are redirected to) is all ones.  On the fused chain the region-max kernel does this itself.
@@ -813,6 +1199,64 @@ static int launch_persistent(K kernel, const RefineParams& p, int threads, size_
 #ifndef UEM_REFINE_COL_VX
 #define UEM_REFINE_COL_VX 2
 #endif
+#ifndef UEM_REFINE_COL2_DSM
+#define UEM_REFINE_COL2_DSM 1
+#endif
+#ifndef UEM_REFINE_COL2_MINB
+#define UEM_REFINE_COL2_MINB 3
+#endif
+#ifndef UEM_REFINE_COL2_NS
+#define UEM_REFINE_COL2_NS 5   // rows in flight per warp: the gather of row it+1 needs that row landed, 3 more stay in flight
+#endif
+// second form of the column walk (pixel-pair packing; see refine_col2_kernel).  UEM_REFINE_KERNEL=col in the environment
+// selects the first form (A/B runs and the bit-equality test of the two forms).
+template <int C>
+static int launch_refine_col2(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
+    constexpr int NT = UEM_REFINE_COL_NT, NS = UEM_REFINE_COL2_NS, DSM = UEM_REFINE_COL2_DSM, MINB = UEM_REFINE_COL2_MINB;
+    *done = false;
+    constexpr float kL2E = 1.4426950408889634f;
+    p.map_scale[0] = kL2E;
+    p.map_scale[1] = p.map_scale[2] = (float)(1.4426950408889634 / (double)p.temp);
+    int ncols_max = (int)(63 * p.sx) + 3;   // low-res columns a warp's 64 image columns can span (+1 for the right neighbour)
+    if (ncols_max > p.w) ncols_max = p.w;
+    const size_t smem = (size_t)NS * NT * 2 * (4 * C + 8) + (DSM ? (size_t)NT * 3 * C * 8 : 0) +
+                        (size_t)(NT / 32) * 2 * ncols_max * 3 * cp_of(C) * 4;
+    if (smem > 100 * 1024 || (int64_t)p.H * p.W >= ((int64_t)1 << 31)) return 0;   // the first form / generic kernels take it
+    auto kernel = refine_col2_kernel<C, NT, NS, DSM, MINB>;
+    if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int nstrips = (p.W + NT * 2 - 1) / (NT * 2);
+    const int64_t total = (int64_t)p.b * nstrips * p.H;
+    const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    UEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, ncols_max));
+    *done = true;
+    return 0;
+}
+
+#ifndef UEM_REFINE_DEFAULT_FORM
+#define UEM_REFINE_DEFAULT_FORM 1   // measured on B200 (profiles/r02_kbench_refine_forms.txt): the first form is still the faster one
+#endif
+static int g_refine_form = -1;   // 0 = second form (pixel-pair packing), 1 = first form (class-pair packing)
+static bool refine_first_form() {
+    if (g_refine_form < 0) {
+        const char* e = getenv("UEM_REFINE_KERNEL");
+        g_refine_form = (e && strcmp(e, "col2") == 0) ? 0 : UEM_REFINE_DEFAULT_FORM;
+    }
+    return g_refine_form == 1;
+}
+
 template <int C>
 static int launch_refine_col(RefineParams p, cudaStream_t st, bool pdl, bool* done) {
     // two columns per lane while their state fits 168 registers (c <= 6); 7 and 8 classes would spill: one column
@@ -900,7 +1344,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
         uem_take_profile_events(&ev0, &ev1);
         if (ev0) UEM_CUDA(cudaEventRecord((cudaEvent_t)ev0, st));
         bool done = false;
-        if (colwalk) rc = launch_refine_col<C>(p, st, pdl && weights_ready && !ev0, &done);
+        if (colwalk && !refine_first_form()) rc = launch_refine_col2<C>(p, st, pdl && weights_ready && !ev0, &done);
+        if (colwalk && !done && rc == 0) rc = launch_refine_col<C>(p, st, pdl && weights_ready && !ev0, &done);
         if (!done && rc == 0) {
             const int vecw = vec ? 4 : 1;
             const size_t smem = (size_t)(w + 2) * Lay<C>::STRIDE * 4 + (size_t)C * kRefineThreads * vecw * 4 + (size_t)kRefineThreads * vecw * 8;
@@ -916,6 +1361,12 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
 }
 
 }  // namespace
+
+extern "C" int uem_set_option(const char* name, int value) {
+    UEM_REQUIRE(name, "uem_set_option: NULL name");
+    if (strcmp(name, "refine_form") == 0) { g_refine_form = value < 0 ? -1 : (value ? 1 : 0); return 0; }   // -1: back to the default
+    return uem_fail("uem_set_option: unknown option '%s'", name);
+}
 
 extern "C" int64_t uem_class_stats_bytes(int b, int c) { return align16((int64_t)b * (c + 2) * 4); }
 
@@ -1016,6 +1467,15 @@ extern "C" int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const fl
                               (cudaStream_t)stream);
 }
 
+extern "C" int uem_mine_proto_phase_f32(const float* feat, int k, const float* protos, int b, int c, int H, int W, int h, int w,
+                                        int64_t R, float eps, void* ws, void* stream) {
+    UEM_REQUIRE(ws && feat && protos && b > 0 && k > 0 && h > 0 && w > 0, "uem_mine_proto_phase_f32: bad arguments");
+    (void)H;
+    char* base = (char*)ws;
+    const MineLayout L = mine_layout(b, c, W, h, w, k, R);
+    return uem_pearson_dist_nchw_f32(feat, b, k, (int64_t)h * w, protos, c, eps, 1, (float*)(base + L.simi), base + L.pearson, stream);
+}
+
 // Side stream of the fused chain: the feature-map pass (Pearson similarity) and the soft/superpixel pass (region
 // maxima) are independent until the refine kernel, so they are forked onto two streams and joined with events
 // (capturable: inside a CUDA graph they become two parallel branches).  One set per host thread and device.
@@ -1052,7 +1512,8 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
                                           float* entropy, float* weight, void* ws, void* stream) {
     UEM_REQUIRE(ws && soft && refined, "uem_mine_refine_select_f32: bad arguments");
     const bool regions_ready = (views & UEM_VIEW_REGIONS_READY) != 0;   // uem_mine_region_phase_f32 already ran on this ws
-    views &= ~UEM_VIEW_REGIONS_READY;
+    const bool simi_ready = (views & UEM_VIEW_SIMI_READY) != 0;         // uem_mine_proto_phase_f32 already ran on this ws
+    views &= ~(UEM_VIEW_REGIONS_READY | UEM_VIEW_SIMI_READY);
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
     const MineLayout L = mine_layout(b, c, W, h, w, k, R);
@@ -1075,8 +1536,9 @@ extern "C" int uem_mine_refine_select_f32(int views, const float* feat, int k, c
     if (!selfclean) UEM_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, (size_t)(L.zero_end - L.zero_begin), st));
     // fork: the feature pass runs on the side stream while the region-max pass (below) runs on the caller's stream
     SideStream* side = nullptr;
-    const bool fork = (views & UEM_VIEW_PROTO) && (views & UEM_VIEW_SUP);
-    if (views & UEM_VIEW_PROTO) {
+    UEM_REQUIRE(!simi_ready || (views & UEM_VIEW_PROTO), "uem_mine_refine_select_f32: UEM_VIEW_SIMI_READY needs the prototype view");
+    const bool fork = (views & UEM_VIEW_PROTO) && (views & UEM_VIEW_SUP) && !simi_ready;
+    if ((views & UEM_VIEW_PROTO) && !simi_ready) {
         UEM_REQUIRE(feat && protos, "uem_mine_refine_select_f32: prototype view needs feat and prototypes");
         void* pst = stream;
         if (fork) {

@@ -76,8 +76,27 @@ def region_phase(soft, sup, temp, num_regions, ws, h, w, k):
     return ws[off:off + 8].view(torch.int64)
 
 
+def proto_phase(feat, prototypes, soft_shape, num_regions, ws, eps=1e-7):
+    """The prototype half of the chain on its own: 1/Pearson distance of ``feat`` (b,k,h,w) to the prototype bank into the
+    similarity slot of ``ws`` (alignment.py:215-217).  It depends on the prototype bank only, so a pipelined loop runs it as
+    soon as the previous step's EMA is done, next to that step's refine / selection kernels; the matching
+    ``refine_select(..., simi_ready=True)`` then skips it."""
+    L.require_cuda(feat, prototypes, ws)
+    feat = L.f32c(feat.detach())
+    prototypes = L.f32c(prototypes.detach())
+    b, c, H, W = soft_shape
+    _, k, h, w = feat.shape
+    assert prototypes.shape == (c, k) and feat.shape[0] == b
+    lib = L.bind(feat)
+    R = max(int(num_regions), 1)
+    assert ws.numel() >= lib.uem_mine_ws_bytes(b, c, H, W, h, w, k, R), "workspace too small: mining.mine_workspace(...)"
+    L.check(lib.uem_mine_proto_phase_f32(L.ptr(feat), k, L.ptr(prototypes), b, c, H, W, h, w, R, ops.f32(eps), L.ptr(ws),
+                                         L.stream_of(feat)))
+
+
 def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pred2=None, sup=None, num_regions=None,
-                  ignored_id=None, eps=1e-7, select=None, ws=None, uvem=None, want_entropy=False, regions_ready=False):
+                  ignored_id=None, eps=1e-7, select=None, ws=None, uvem=None, want_entropy=False, regions_ready=False,
+                  simi_ready=False):
     """Returns (refined (b,c,H,W) fp32, hard (b,H,W) int64 or None); with ``uvem``/``want_entropy`` the tuple
     grows to (refined, hard, entropy (b*H*W,) or None, uvem_weight (b*H*W,) or None), all from the same pass.
 
@@ -87,7 +106,8 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
         (one 8-byte device->host copy, like torch_scatter's ``int(index.max())+1``).
     ignored_id: optional (1,) int64 device tensor holding the batch-global max id (e.g. after an
         all_reduce(MAX) across ranks); None -> computed from ``sup`` inside the call.
-    regions_ready: ``region_phase`` already ran on ``ws`` for this batch (needs ``num_regions``, ``ignored_id``, ``ws``)."""
+    regions_ready: ``region_phase`` already ran on ``ws`` for this batch (needs ``num_regions``, ``ignored_id``, ``ws``).
+    simi_ready: ``proto_phase`` already ran on ``ws`` for this batch (``feat`` is still passed: it carries the shapes)."""
     L.require_cuda(soft, feat, prototypes, pred1, pred2, sup, ignored_id)
     soft = L.f32c(soft.detach())
     b, c, H, W = soft.shape
@@ -136,11 +156,14 @@ def refine_select(views, soft, temp, feat=None, prototypes=None, pred1=None, pre
     if regions_ready:
         assert num_regions is not None and ignored_id is not None and ws is not None and (views & ops.VIEW_SUP)
         views = int(views) | ops.VIEW_REGIONS_READY
+    if simi_ready:
+        assert ws is not None and (views & ops.VIEW_PROTO)
+        views = int(views) | ops.VIEW_SIMI_READY
     L.check(lib.uem_mine_refine_select_f32(
         int(views), L.ptr(feat), k, L.ptr(prototypes), L.ptr(pred1), L.ptr(pred2), h, w, L.ptr(sup), R, L.ptr(ignored_id),
         L.ptr(soft), b, c, H, W, ops.f32(temp), ops.f32(eps), ops.f32(top), ops.f32(low), int(ign), L.ptr(refined),
         L.ptr(hard), uv, L.ptr(ent), L.ptr(wgt), L.ptr(ws), L.stream_of(soft)))
-    if config.strict_asserts:
+    if config.strict_asserts and (int(views) & ops.VIEW_SUP):
         _raise_on_status(ws, "label_refine")
     # [class maxima | -min | bad] of `refined`, reused by pseudo_selection() so it needs no second max pass
     if select is None:  # the drop-in pairing label_refine -> pseudo_selection: hand the class statistics over

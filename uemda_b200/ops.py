@@ -14,6 +14,7 @@ from . import config
 
 VIEW_PROTO, VIEW_PRED, VIEW_SUP = 1, 2, 4
 VIEW_REGIONS_READY = 8  # uem_mine_refine_select_f32 only: mining.region_phase already ran on the workspace
+VIEW_SIMI_READY = 16    # uem_mine_refine_select_f32 only: mining.proto_phase already ran on the workspace
 REDUCE = {"sum": 0, "add": 0, "max": 1, "mean": 2}
 MODE_VIEWS = {"all": VIEW_PROTO | VIEW_PRED | VIEW_SUP, "p": VIEW_PROTO, "l": VIEW_PRED, "s": VIEW_SUP}
 
