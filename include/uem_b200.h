@@ -273,6 +273,27 @@ UEM_API int uem_pack_local_partials_f64(const void* ws, int b, int c, int k, con
 UEM_API int uem_fold_gathered_f64(const double* gathered, int world, int c, int k, float* sums, int64_t* counts,
                           int64_t* max_id, void* stream);
 
+/* ---- f4: IAST class-wise percentile thresholds + sliding-window accumulation (uemda/utils/tools.py) -----------------
+ * ias_thresh (:323-333) / generate_pseudo (:347-371): probs (b,c,hw) planar fp32 (the model output the reference calls
+ * `logits`).  conf_hist: per class, the EXACT histogram of float16(max prob) over the pixels whose argmax is that class, on
+ * the 65536 half bit patterns ordered like the numbers (hist: uem_iast_hist_bytes(c) bytes, zeroed by the call).
+ * thresholds: per class np.percentile(linear) of [previous threshold] + samples at qfrac_host[c] = q/100 (host doubles:
+ * q = 100*(1 - alpha*w**gamma) is Python arithmetic), written as float32 to tmp_out (optional), then
+ * cls_thresh <- beta*cls_thresh + float32(1-beta)*tmp, values >= 1 -> 0.999 (cls_thresh: device double (c), in/out).
+ * labels: out (b,hw) uint8 = argmax + 1, or 0 where the winning probability < cls_thresh[argmax].
+ * window_accumulate / window_average: pre_slide (:84-97): full[:, :, y1:y2, x1:x2] += tile[:, :, :y2-y1, :x2-x1],
+ * count += 1 (count may be NULL), then full /= count.  views_mean: tta_predict's mean over n stacked views (:149-150). */
+UEM_API int64_t uem_iast_hist_bytes(int c);
+UEM_API int uem_iast_conf_hist_f32(const float* probs, int b, int c, int64_t hw, uint32_t* hist, void* stream);
+UEM_API int uem_iast_thresholds_f64(const uint32_t* hist, int c, const double* qfrac_host, double beta, float one_minus_beta,
+                            double* cls_thresh, float* tmp_out, int64_t* count_out, void* stream);
+UEM_API int uem_iast_labels_u8(const float* probs, int b, int c, int64_t hw, const double* cls_thresh, uint8_t* out,
+                       void* stream);
+UEM_API int uem_window_accumulate_f32(float* full, float* count, const float* tile, int b, int c, int H, int W, int th, int tw,
+                              int y1, int x1, int y2, int x2, void* stream);
+UEM_API int uem_window_average_f32(float* full, const float* count, int b, int c, int64_t hw, void* stream);
+UEM_API int uem_views_mean_f32(const float* views, int n, int64_t numel, float* out, void* stream);
+
 /* ---- device-side exchange over peer-mapped memory (csrc/uem_exchange.cu) -------------------------------
  * The same statistics as above, but stored by a kernel straight into every peer's symmetric region over NVLink, with
  * release/acquire flags instead of a host-issued collective, so a whole sharded step is capturable as CUDA graphs with no

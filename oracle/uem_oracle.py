@@ -419,3 +419,84 @@ def uvem_loss_calc(heads, label, label_soft, m=0.1, threshold=0.7, gamma=8.0, us
         valid = torch.sum((u <= threshold) & (t_ != ignore_label))
         total = total + (weight * ce).sum() / (valid + 1e-7)
     return (total / len(heads) if multi else total), balance_freq
+
+
+# --------------------------------------------------------------------------------------
+# f4: IAST class-wise percentile thresholds + sliding-window accumulation (uemda/utils/tools.py)
+# --------------------------------------------------------------------------------------
+def ias_thresh(conf_dict, n_class, alpha, w=None, gamma=1.0):
+    """tools.py:323-333: per class, np.percentile (linear interpolation) of its confidence list at
+    100 * (1 - alpha * w_c ** gamma); classes whose list is None keep 1.0.  Returns float32 (n_class,)."""
+    import numpy as np
+    if w is None:
+        w = np.ones(n_class)
+    cls_thresh = np.ones(n_class, dtype=np.float32)
+    for c in range(n_class):
+        if conf_dict[c] is not None:
+            cls_thresh[c] = np.percentile(np.array(conf_dict[c]), 100 * (1 - alpha * w[c] ** gamma))
+    return cls_thresh
+
+
+def iast_batch_step(probs, cls_thresh, alpha, beta, gamma):
+    """One batch of generate_pseudo, tools.py:347-371, file IO and visualisation left out.
+    probs (b,c,H,W) float32 torch tensor (the model output the reference calls `logits`), cls_thresh float64 (c,) ndarray
+    (np.ones(c) * 0.9 before the first batch).  Returns (new cls_thresh float64 (c,), labels uint8 (b,H,W) = class + 1,
+    0 where the winning confidence is below its class threshold)."""
+    import numpy as np
+    n_class = probs.shape[1]
+    max_items = probs.max(dim=1)                               # :349  (lowest index on ties)
+    label_pred = max_items[1].numpy()
+    logits_pred = max_items[0].numpy()
+    conf = {c: [cls_thresh[c]] for c in range(n_class)}        # :353  the previous threshold is one sample of the list
+    for c in range(n_class):
+        conf[c].extend(logits_pred[label_pred == c].astype(np.float16))   # :355  float16!
+    tmp = ias_thresh(conf, n_class, alpha, w=cls_thresh, gamma=gamma)     # :357
+    cls_thresh = beta * cls_thresh + (1 - beta) * tmp          # :360  float64 * float + float32 * float -> float64
+    cls_thresh[cls_thresh >= 1] = 0.999                        # :361
+    np_logits = probs.numpy()
+    out = []
+    for i in range(np_logits.shape[0]):
+        logit = np_logits[i].transpose(1, 2, 0)                # :366
+        label = np.argmax(logit, axis=2)
+        amax = np.amax(logit, axis=2)
+        ignore = amax < cls_thresh[label]                      # :369-370 (float32 < float64)
+        label = label + 1
+        label[ignore] = 0
+        out.append(label.astype(np.uint8))
+    return cls_thresh, np.stack(out)
+
+
+def slide_windows(image_hw, tile_size=(512, 512)):
+    """Window origins of pre_slide, tools.py:62-80: overlap 1/2, windows clamped to the image.  Returns [(y1, x1, y2, x2)]."""
+    from math import ceil
+    H, W = image_hw
+    stride = ceil(tile_size[0] * (1 - 1 / 2))
+    rows = int(ceil((H - tile_size[0]) / stride) + 1)
+    cols = int(ceil((W - tile_size[1]) / stride) + 1)
+    wins = []
+    for r in range(rows):
+        for c in range(cols):
+            x1, y1 = int(c * stride), int(r * stride)
+            x2, y2 = min(x1 + tile_size[1], W), min(y1 + tile_size[0], H)
+            x1, y1 = max(int(x2 - tile_size[1]), 0), max(int(y2 - tile_size[0]), 0)
+            wins.append((y1, x1, y2, x2))
+    return wins
+
+
+def slide_accumulate(tiles, wins, image_hw):
+    """pre_slide, tools.py:69-97 with the model call factored out: tiles[i] (b,c,th,tw) is the (padded) prediction of window
+    i; the full map is the per-pixel mean of the windows covering it (sum in window order, then / count)."""
+    b, c = tiles[0].shape[:2]
+    H, W = image_hw
+    full = torch.zeros(b, c, H, W)
+    cnt = torch.zeros(b, 1, H, W)
+    for t, (y1, x1, y2, x2) in zip(tiles, wins):
+        full[:, :, y1:y2, x1:x2] += t[:, :, 0:y2 - y1, 0:x2 - x1]
+        cnt[:, :, y1:y2, x1:x2] += 1
+    full /= cnt
+    return full
+
+
+def tta_mean(preds):
+    """tta_predict, tools.py:132-152 after de-augmentation: mean over the stacked views (cat on dim 0, mean dim 0)."""
+    return torch.mean(torch.cat(preds, 0), dim=0, keepdim=True)

@@ -1057,3 +1057,59 @@ def test_refine_kernel_forms_agree(dev, shape):
         lib.uem_set_option(b"refine_form", -1)
     assert torch.equal(outs[0][0], outs[1][0]), "refined maps of the two kernel forms differ"
     assert torch.equal(outs[0][1], outs[1][1]), "class statistics of the two kernel forms differ"
+
+
+# ------------------------------------------------------------------------------------ f4: IAST thresholds, sliding windows
+def test_iast_golden_thresholds_and_labels(dev):
+    """IAST class-wise percentile thresholds + thresholded labels against the reference's own ias_thresh driven through the
+    per-batch body of generate_pseudo (tests/golden/iast_small.npz): thresholds (float64 state and the float32 percentile)
+    and uint8 label maps bit for bit over three chained batches, one of them with a class that (almost) never wins."""
+    import os
+    from uemda_b200.utils.tools import IASTSelector
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "iast_small.npz"))
+    alpha, beta, gamma = [float(v) for v in z["iast_params"]]
+    sel = IASTSelector(n_class=z["in_probs_0"].shape[1], pl_alpha=alpha, pl_beta=beta, pl_gamma=gamma, device=dev)
+    for step in range(3):
+        assert np.array_equal(sel.cls_thresh.cpu().numpy(), z["in_thresh_%d" % step]), "threshold state entering batch %d" % step
+        labels = sel.step(torch.from_numpy(z["in_probs_%d" % step]).to(dev))
+        assert np.array_equal(sel.tmp_thresh.cpu().numpy(), z["out_tmp_thresh_%d" % step]), "percentiles of batch %d" % step
+        assert np.array_equal(sel.cls_thresh.cpu().numpy(), z["out_thresh_%d" % step]), "thresholds after batch %d" % step
+        assert np.array_equal(labels.cpu().numpy(), z["out_labels_%d" % step]), "labels of batch %d" % step
+
+
+@pytest.mark.parametrize("shape,scale", [((2, 7, 96, 128), 3.0), ((1, 6, 33, 47), 1.0), ((4, 3, 64, 64), 8.0), ((8, 6, 512, 512), 2.0)])
+def test_iast_vs_oracle_shapes(dev, shape, scale):
+    """The same against the oracle restatement (np.percentile over float16 lists) at ragged and full config-2 shapes, two
+    chained batches; per-class sample counts equal the argmax histogram."""
+    from oracle import uem_oracle as O
+    from uemda_b200.utils.tools import IASTSelector
+    b, c, H, W = shape
+    g = torch.Generator().manual_seed(b * 100 + W)
+    sel = IASTSelector(n_class=c, pl_alpha=0.2, pl_beta=0.9, pl_gamma=8.0, device=dev)
+    thr = np.ones(c) * 0.9
+    for step in range(2):
+        probs = torch.softmax(torch.randn(b, c, H, W, generator=g) * scale, dim=1)
+        thr, want = O.iast_batch_step(probs, thr, 0.2, 0.9, 8.0)
+        got = sel.step(probs.to(dev))
+        assert np.array_equal(sel.cls_thresh.cpu().numpy(), thr), "thresholds, batch %d: %s vs %s" % (step, sel.cls_thresh.cpu().numpy(), thr)
+        assert np.array_equal(got.cpu().numpy(), want), "labels, batch %d" % step
+        assert np.array_equal(sel.counts.cpu().numpy(), np.bincount(probs.argmax(dim=1).reshape(-1).numpy(), minlength=c))
+
+
+def test_sliding_window_golden(dev):
+    """pre_slide (tools.py:61-97) against the reference's own run with a stand-in model that replays the golden tiles."""
+    import os
+    from uemda_b200.utils import tools as T
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "iast_small.npz"))
+    H, W, th, tw = [int(v) for v in z["slide_meta"]]
+    tiles = [torch.from_numpy(t).to(dev) for t in z["slide_tiles"]]
+    it = iter(tiles)
+    image = torch.zeros(tiles[0].shape[0], 3, H, W, device=dev)
+    full = T.pre_slide(lambda x: next(it), image, num_classes=tiles[0].shape[1], tile_size=(th, tw), tta=False)
+    _eq(full, torch.from_numpy(z["slide_out"]), "pre_slide")
+    # TTA mean: 8 views of a model that is equivariant (identity) average back to the input
+    x = torch.rand(1, 4, 32, 32, device=dev)
+    assert_close(T.tta_predict(lambda a: a, x), x, rtol=1e-6, atol=1e-7, what="tta of the identity")
+    from oracle import uem_oracle as O
+    views = [torch.rand(1, 4, 16, 16) for _ in range(8)]
+    assert_close(T.views_mean([v.to(dev) for v in views]), O.tta_mean(views), rtol=1e-6, atol=1e-7, what="views mean")

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--sets", type=int, default=3)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--only", default="")
-    ap.add_argument("--refine-form", type=int, default=0, help="0 = pixel-pair column walk (default), 1 = first form")
+    ap.add_argument("--refine-form", type=int, default=-1, help="0 = pixel-pair packed column walk, 1 = first form, -1 = library default")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     dev = torch.device("cuda", 0)

@@ -74,6 +74,13 @@ SIGNATURES = {
     "uem_pack_local_f64": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "uem_pack_local_partials_f64": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "uem_fold_gathered_f64": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "uem_iast_hist_bytes": (_L, [_I]),
+    "uem_iast_conf_hist_f32": (_I, [_P, _I, _I, _L, _P, _P]),
+    "uem_iast_thresholds_f64": (_I, [_P, _I, _P, _c.c_double, _F, _P, _P, _P, _P]),
+    "uem_iast_labels_u8": (_I, [_P, _I, _I, _L, _P, _P, _P]),
+    "uem_window_accumulate_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "uem_window_average_f32": (_I, [_P, _P, _I, _I, _L, _P]),
+    "uem_views_mean_f32": (_I, [_P, _I, _L, _P, _P]),
     "uem_xchg_region_bytes": (_L, [_I, _I, _I, _I]),
     "uem_xchg_send_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "uem_xchg_wait_maxid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
