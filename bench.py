@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of a CPU leg")
     ap.add_argument("--refine-form", type=int, default=None, help="development: 0 / 1 = form of the fused refine kernel")
+    ap.add_argument("--opt", action="append", default=[], help="development: name=value for uem_set_option (repeatable)")
+    ap.add_argument("--force-peer", action="store_true", help="development: N = 1 with the peer exchange kernels in the loop")
+    ap.add_argument("--timeline", action="store_true", help="development: print the serial per-part timeline to stderr")
     return ap.parse_args()
 
 
@@ -312,10 +315,15 @@ class Pipeline:
         self.ignored = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.n)]
         self.outs = [None] * self.n
         # the target chain is the critical path: high-priority stream; phase A fills the gaps from low-priority streams
-        self.main = torch.cuda.Stream(device=dev, priority=-1)
-        self.br_proto = torch.cuda.Stream(device=dev, priority=-1)   # the next step's refine kernel waits for this one
-        self.br_region = torch.cuda.Stream(device=dev, priority=0)
-        self.br_source = torch.cuda.Stream(device=dev, priority=0)
+        # N > 1: the region / source branches end in the exchange send, which the OTHER ranks wait for: they go first
+        # (measured, one GPU, us per step: lhhl 98.4, lhll 98.4, hhhh 102.2, lhhh 106.3, hlhh 106.9, llhh 114.1)
+        hi, lo = (-1, 0)
+        pm = os.environ.get("UEM_BENCH_PRIO", "lhhl")   # main, proto, region, source: h(igh) / l(ow); development knob
+        pr = [hi if ch == "h" else lo for ch in pm]
+        self.main = torch.cuda.Stream(device=dev, priority=pr[0])
+        self.br_proto = torch.cuda.Stream(device=dev, priority=pr[1])   # the next step's refine kernel waits for this one
+        self.br_region = torch.cuda.Stream(device=dev, priority=pr[2])
+        self.br_source = torch.cuda.Stream(device=dev, priority=pr[3])
         self.use_graph = use_graph
         self.graphs = None
         self.peer = miner.peer if miner is not None else None
@@ -333,8 +341,10 @@ class Pipeline:
         self.local_ids[j] = self.mining.region_phase(s["soft"], s["sup"], TEMP, self.R, self.ws[j], self.wl.h, self.wl.w, self.wl.k)
 
     def send_part(self, j):
+        """N > 1: this rank's statistics of step j into every rank's slot; the same launch polls the other ranks' max ids
+        and leaves the batch-global ignored id (alignment.py:241) in a static tensor, one step ahead of its consumer."""
         if self.peer is not None:
-            self.miner.send_stats(self.partials[j], self.local_ids[j], j % self.peer.depth)
+            self.miner.send_stats(self.partials[j], self.local_ids[j], j % self.peer.depth, global_id_out=self.ignored[j])
 
     def ema_part(self, j):
         """prototype EMA of step j (alignment.py:347-353): its last reader (the Pearson pass of step j) ran one step earlier"""
@@ -348,52 +358,77 @@ class Pipeline:
         s = self.sets[j]
         self.mining.proto_phase(s["feat"], self.proto_state, s["soft"].shape, self.R, self.ws[j], eps=self.al.eps)
 
-    def id_part(self, j):
-        if self.peer is not None:
-            return self.miner.receive_id(j % self.peer.depth, out=self.ignored[j])
-        return self.local_ids[j]   # one rank: the local max id is the global one
+    def ignored_of(self, j):
+        return self.ignored[j] if self.peer is not None else self.local_ids[j]   # one rank: the local max id is the global one
 
-    def refine_part(self, j, ignored):
+    def refine_part(self, j):
         s = self.sets[j]
         out = self.mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=self.proto_state, pred1=s["pred1"],
-                                        pred2=s["pred2"], sup=s["sup"], num_regions=self.R, ignored_id=ignored, eps=self.al.eps,
-                                        select=(CUTOFF[0], CUTOFF[1], -1), ws=self.ws[j], uvem=UVEM, regions_ready=True,
-                                        simi_ready=True)
+                                        pred2=s["pred2"], sup=s["sup"], num_regions=self.R, ignored_id=self.ignored_of(j),
+                                        eps=self.al.eps, select=(CUTOFF[0], CUTOFF[1], -1), ws=self.ws[j], uvem=UVEM,
+                                        regions_ready=True, simi_ready=True)
         self.outs[j] = out
         return out
 
     def step_body(self, j, serial=False):
         """Step j = refine + selection of set j on the current stream, with everything that does not depend on them as
         parallel branches (fork / join): [EMA of step j -> Pearson of set j+1], [region phase of set j+1], [source
-        statistics of set j+1], then the exchange send of set j+1.  Same results as running the steps back to back: the
-        Pearson pass of step j+1 reads the bank right after the EMA of step j, as it would there.
+        statistics of set j+1], then the exchange send (+ the poll for the global id) of set j+1.  Same results as running
+        the steps back to back: the Pearson pass of step j+1 reads the bank right after the EMA of step j, as it would there.
         serial: one after the other on the current stream (kernel-level timing: the timed kernel runs alone)."""
         cur = torch.cuda.current_stream(self.dev)
         jn = (j + 1) % self.n
         if serial:
-            self.refine_part(j, self.id_part(j))
+            self.refine_part(j)
             self.ema_part(j)
             self.proto_part(jn)
             self.region_part(jn)
             self.source_part(jn)
             self.send_part(jn)
             return
-        self.br_region.wait_stream(cur)
-        self.br_source.wait_stream(cur)
-        ignored = self.id_part(j)          # N > 1: blocks this stream until every rank's statistics of step j are here
-        self.br_proto.wait_stream(cur)
-        with torch.cuda.stream(self.br_proto):
-            self.ema_part(j)
-            self.proto_part(jn)
+        for st in (self.br_region, self.br_source, self.br_proto):
+            st.wait_stream(cur)
         with torch.cuda.stream(self.br_source):
             self.source_part(jn)
         with torch.cuda.stream(self.br_region):
             self.region_part(jn)
             self.br_region.wait_stream(self.br_source)
             self.send_part(jn)
-        self.refine_part(j, ignored)
+        with torch.cuda.stream(self.br_proto):
+            self.ema_part(j)
+            self.proto_part(jn)
+        self.refine_part(j)
         cur.wait_stream(self.br_proto)
         cur.wait_stream(self.br_region)
+
+    def timeline(self, steps=12):
+        """development aid: the parts of a step run one after the other on the main stream with a CUDA event between them;
+        returns {part: mean microseconds} (no overlap, every part pays its own launch ramp and tail)."""
+        names = ["refine+select", "ema", "proto", "region", "source", "send"]
+        acc = {k: 0.0 for k in names}
+        with torch.cuda.stream(self.main):
+            for _ in range(steps):
+                j = self.pos % self.n
+                jn = (j + 1) % self.n
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                ev[0].record()
+                self.refine_part(j)
+                ev[1].record()
+                self.ema_part(j)
+                ev[2].record()
+                self.proto_part(jn)
+                ev[3].record()
+                self.region_part(jn)
+                ev[4].record()
+                self.source_part(jn)
+                ev[5].record()
+                self.send_part(jn)
+                ev[6].record()
+                self.pos += 1
+                torch.cuda.synchronize()
+                for i, k in enumerate(names):
+                    acc[k] += ev[i].elapsed_time(ev[i + 1]) * 1e3 / steps
+        return acc
 
     def prime(self):
         """phase A of set 0 (what the previous step would have done); the pipeline then stays in sequence: step i runs
@@ -616,6 +651,9 @@ def main():
     lib = _lib.load()
     if args.refine_form is not None:
         _lib.check(lib.uem_set_option(b"refine_form", args.refine_form))
+    for kv in args.opt:
+        name, val = kv.split("=")
+        _lib.check(lib.uem_set_option(name.encode(), int(val)))
     config.strict_asserts = False
 
     inp, sets, capacity = make_sets(wl, args.sets, dev, rank, world)
@@ -628,6 +666,13 @@ def main():
         al.prototypes = inp["prototypes"].to(dev)
         al.downscale_gt = DownscaleLabel(wl.scale, wl.c, -1, 0.75)
         miner = mining.ShardedMiner(al, exchange=args.exchange, depth=min(args.sets, 4))
+    elif args.force_peer:
+        from uemda_b200.exchange import PeerExchange
+        al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c, ignore_label=-1, decay=DECAY)
+        al.prototypes = inp["prototypes"].to(dev)
+        al.downscale_gt = DownscaleLabel(wl.scale, wl.c, -1, 0.75)
+        miner = mining.ShardedMiner(al, exchange="nccl")
+        miner.peer = PeerExchange.local_only(1, wl.c, wl.k, depth=min(args.sets, 4), device=dev)[0]
 
     def barrier():
         if world > 1:
@@ -672,6 +717,12 @@ def main():
             except Exception:  # noqa: BLE001
                 pass
         refine_ms = statistics.mean(kern) if kern else None
+
+    if args.timeline and pipe is not None:
+        tl = pipe.timeline()
+        if rank == 0:
+            print("timeline (us, serial): " + ", ".join("%s %.1f" % kv for kv in tl.items()) + "; sum %.1f" % sum(tl.values()), file=sys.stderr)
+        barrier()
 
     # ---- N > 1: sharded result == one-GPU result over the concatenated batch (outside the timed region)
     parity = None
@@ -882,6 +933,9 @@ def sharded_parity(wl, inp, sets, capacity, miner, pipe, dev, rank, world, args)
     # sharded: 3 eager steps from the initial bank
     init = inp["prototypes"].to(dev)
     bank.copy_(init)
+    if pipe is not None:   # the Pearson pass of the next step was issued one step ago, against the old bank: redo it
+        with torch.cuda.stream(pipe.main):
+            pipe.proto_part(pipe.pos % pipe.n)
     torch.cuda.synchronize()
     dist.barrier()
     hard_first = None

@@ -305,16 +305,20 @@ UEM_API int uem_views_mean_f32(const float* views, int n, int64_t numel, float* 
  * depth <= 4 slots are used round-robin by the caller (slot = step % depth); world <= 16.
  * send: folds the per-image partials uem_proto_accum_nchw_f32 left in partials_ws (sums == NULL form) in image order and
  *   stores the vector into slot [slot][rank] of every peer; waits (bounded) for the peers' acknowledgement of the
- *   previous use of that slot first.
+ *   previous use of that slot first.  global_id_out (optional): the same launch then also polls the other ranks' max ids of
+ *   this step and writes the batch-global max id there (what wait_maxid would return), saving that launch.
  * wait_maxid: blocks the stream (bounded spin in a one-warp kernel) until every rank's vector of this slot has arrived;
  *   writes the batch-global max id.  fold_finalize_ema: (after wait_maxid on the same stream) folds the ranks in rank
  *   order -> keep-old rule -> EMA (alignment.py:347-353,463-466; proto_new may alias proto_old; NULL = no EMA), optional
  *   folded sums (c,k) / counts (c) / histogram (c+1) outputs; acknowledges the slot to every peer.
- * uem_xchg_status: synchronises the stream and returns the region's status word: bit 8 = a spin timed out (2 s; a peer
- *   is gone or the calls are not issued in lockstep), bit 16 = fold_finalize ran before its vectors had arrived. */
+ * Every payload word travels as one 8-byte {word, sequence number} store (no fences or flags on the data path); the
+ * consumers poll the words they read.
+ * uem_xchg_status: synchronises the stream and returns the region's status word: bit 8 = a poll timed out (2 s: a peer
+ *   is gone, or the calls are not issued in lockstep on every rank). */
 UEM_API int64_t uem_xchg_region_bytes(int world, int depth, int c, int k);
 UEM_API int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
-                      const void* const* peer_regions, int rank, int world, int depth, int slot, void* stream);
+                      const void* const* peer_regions, int rank, int world, int depth, int slot, int64_t* global_id_out,
+                      void* stream);
 UEM_API int uem_xchg_wait_maxid(void* region, int world, int depth, int slot, int c, int k, int64_t* max_id_out, void* stream);
 UEM_API int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, int rank, int world, int depth, int slot, int c,
                                    int k, const float* proto_old, float eps, float one_minus_decay, float decay,

@@ -992,8 +992,10 @@ def test_peer_exchange_emulated_ranks(dev, world, depth):
         ids = [torch.randint(0, 1 << 40, (1,), generator=g).to(dev) for _ in range(world)]
         hists = [ops.class_hist(labs[r], c) for r in range(world)]
         parts = [ops.proto_accumulate(feats[r], labs[r], c, -1, fold=False) for r in range(world)]
-        for r in range(world):
-            xs[r].send(parts[r], ids[r], slot, hist=hists[r])
+        gid = torch.zeros(1, dtype=torch.int64, device=dev)
+        for r in range(world):   # the last sender finds every other rank's id already there: it may poll for the global id
+            xs[r].send(parts[r], ids[r], slot, hist=hists[r], global_id_out=gid if r == world - 1 else None)
+        assert int(gid) == max(int(i) for i in ids), "global id from the fused send"
         got_ids, got_hist = [], []
         for r in range(world):
             got_ids.append(xs[r].wait_max_id(slot))
@@ -1021,13 +1023,14 @@ def test_peer_exchange_emulated_ranks(dev, world, depth):
             assert torch.equal(sums0, s1)
 
 
-def test_peer_exchange_reports_a_missing_fold(dev):
-    """fold_finalize before its vectors have arrived must flag status bit 16 instead of folding garbage silently."""
+def test_peer_exchange_reports_a_missing_send(dev):
+    """A consumer whose vectors never arrive must give up after its bounded poll (2 s) and flag status bit 8 -- an error
+    code, not a hung GPU."""
     from uemda_b200.exchange import PeerExchange
     xs = PeerExchange.local_only(2, 3, 64, depth=2, device=dev)
     bank = torch.zeros(3, 64, device=dev)
     xs[0].fold_finalize(0, bank, decay=0.9)
-    assert xs[0].status() & 16
+    assert xs[0].status() & 8
 
 
 @pytest.mark.parametrize("shape", [(2, 6, 96, 256, 6, 16), (1, 7, 64, 192, 4, 12), (2, 5, 72, 200, 9, 25), (1, 8, 64, 256, 4, 16),

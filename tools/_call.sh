@@ -1,6 +1,13 @@
-K="--only label_refine,mine_chain --iters 120"
-echo "== form1 default (MINB 3) cfg2" > gpurun_out/r2_kb_refine4.txt; python tools/kbench.py $K --refine-form 1 >> gpurun_out/r2_kb_refine4.txt 2>&1
-echo "== variant a: form1 MINB=2 cfg2" >> gpurun_out/r2_kb_refine4.txt; UEM_B200_LIB=$PWD/uemda_b200/libuem_b200_a.so python tools/kbench.py $K --refine-form 1 >> gpurun_out/r2_kb_refine4.txt 2>&1
-for t in b c d; do echo "== variant $t cfg2" >> gpurun_out/r2_kb_refine4.txt; UEM_B200_LIB=$PWD/uemda_b200/libuem_b200_$t.so python tools/kbench.py $K --refine-form 0 >> gpurun_out/r2_kb_refine4.txt 2>&1; done
-export UEM_B200_LIB=$PWD/uemda_b200/libuem_b200_c.so
-python tools/kbench.py --only label_refine --iters 24 --refine-form 0 > gpurun_out/plain4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:refine_col2 -s 4 -c 2 -o gpurun_out/prof_col2_r02c python tools/kbench.py --only label_refine --iters 24 --refine-form 0 > gpurun_out/ncu4.log 2>&1
+python -m pytest tests -m gpu -x -q -k "peer_exchange" 2>&1 | tail -3
+export NCCL_DEBUG=WARN
+N=${NGPU:-2}
+B="--steps 40 --warmup 10 --no-extra --no-e2e --no-cpu-baseline"
+python bench.py $B > gpurun_out/tmp.json 2> gpurun_out/tmp.err; python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/tmp.json') if l.startswith('{')][-1]); print('1gpu', round(d['value']), round(d['ms_per_step']*1e3,1))" >> gpurun_out/r2_prio3.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 40 --warmup 10 --no-e2e > gpurun_out/r2_bench_${N}gpu_c.json 2> gpurun_out/r2_bench_${N}gpu_c.err
+echo "${N}gpu rc=$?" >> gpurun_out/r2_prio3.txt; tail -c 300 gpurun_out/r2_bench_${N}gpu_c.err | tr '\n' ' ' >> gpurun_out/r2_prio3.txt
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_${N}gpu_c.json') if l.startswith('{')][-1]); print('${N}gpu', round(d['value']), round(d['ms_per_step']*1e3,1), d['impl_detail']['exchange'], d['impl_detail']['exchange_status'], d['kernels_per_step'], json.dumps(d.get('parity'))[:330])" >> gpurun_out/r2_prio3.txt
+cat gpurun_out/r2_prio3.txt

@@ -12,6 +12,9 @@
 #define UEM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 int uem_fail(const char* fmt, ...);
+// tuning knobs set through uem_set_option (0 = the kernel's own choice); see uem_api.cu
+extern int g_uem_refine_ctas_per_sm;   // cap on resident CTAs per SM of the fused refine kernel (co-residency with the next batch's streaming kernels)
+extern int g_uem_region_ctas_per_sm;   // same for the region-max kernel
 void uem_note_launches(int n);  // bookkeeping for uem_kernel_launches()
 void uem_take_profile_events(void** start, void** stop);
 

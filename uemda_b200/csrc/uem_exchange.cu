@@ -4,30 +4,35 @@
 //   * prototype partial sums (c,k) fp32 + counts (c) int64          alignment.py:347-353 (sums over the WHOLE batch)
 //   * class histogram (c) + valid count, int64                      balance.py:45-52 (batch-global label frequencies)
 //   * the rank-local max superpixel id, int64                       alignment.py:241 (batch-global "ignored" id)
-// ~48 KiB at c = 6, k = 2048.  Instead of a host-issued NCCL all-gather between two CUDA graphs, every rank STORES its
-// vector straight into a slot of every peer's symmetric region (peer-mapped device memory: torch symmetric memory or
-// cudaIpc handles) followed by a release flag, and the consumer side acquires the flags in a kernel of its own graph:
+// ~48 KiB of payload at c = 6, k = 2048.  Instead of a host-issued NCCL all-gather between two CUDA graphs, every rank
+// STORES its vector straight into a slot of every peer's symmetric region (peer-mapped device memory: torch symmetric
+// memory or cudaIpc handles), and the consumers are kernels of the peer's own graph.
+//
+// Protocol: every 32-bit payload word travels as ONE 8-byte store {word, sequence number} (the "LL" idea of NCCL's
+// low-latency protocol): an 8-byte store is a single transaction, so a reader that sees the expected sequence number in
+// the upper half holds valid data in the lower half -- no fences, no separate flags, no arrival counters on the data
+// path.  (A first version with __threadfence_system + release flags cost ~18 us per step: system-scope fences issued while
+// the other kernels of the step saturate the memory system are slow.)  Payload doubles to ~96 KiB per peer, still latency.
 //
 //   uem_xchg_send_f32            grid (chunks, world): CTA (ch, p) folds chunk ch of this rank's per-image partials in
-//                                image order and stores it into peer p's slot [slot][rank]; the last chunk CTA of peer p
-//                                publishes data_flag[slot][rank] = sequence number on p (st.release.sys).
-//   uem_xchg_wait_maxid          one warp: lane r acquires data_flag[slot][r], then the batch-global max id = max over
-//                                the ranks' ids (needed by the refine kernel, so this sits at the head of phase B).
-//   uem_xchg_fold_finalize_ema   folds the world slots in RANK ORDER (identical fp32 additions on every rank -> the
-//                                replicated prototype bank stays bit-identical), local mean, keep-old rule, EMA; the last
-//                                CTA acknowledges the slot to every peer (ack_flag[slot][rank] on the peer), which is
-//                                what a sender waits for before it overwrites that slot `depth` steps later.
+//                                image order and stores {value, seq} pairs into peer p's slot [slot][rank].
+//   uem_xchg_wait_maxid          one warp: lane r polls rank r's max-id words -> batch-global max id (needed by the
+//                                refine kernel, so this heads the step's main branch).
+//   uem_xchg_fold_finalize_ema   every thread polls its own words of all ranks (normally already there), folds them in
+//                                RANK ORDER (identical fp32 additions on every rank -> the replicated prototype bank stays
+//                                bit-identical), local mean, keep-old rule, EMA; the last CTA acknowledges the slot to every
+//                                peer (one release store per peer), which is what a sender checks before it overwrites that
+//                                slot `depth` steps later.
 // No kernel waits for a kernel that is queued behind it on its own GPU: a send of step s waits for the acks of step
-// s - depth, a wait of step s for the sends of step s -- both are upstream in every rank's stream order, so the scheme
-// cannot deadlock however the ranks drift.  Every spin is bounded (2 s of %globaltimer): on a timeout status bit 8 is set
-// in the region header and the kernel carries on, so a lost peer shows up as an error code, not as a hung GPU.
+// s - depth, the consumers of step s for the sends of step s -- both are upstream in every rank's stream order, so the
+// scheme cannot deadlock however the ranks drift.  Every poll is bounded (2 s of %globaltimer): on a timeout status bit 8
+// is set in the region header and the kernel carries on, so a lost peer shows up as an error code, not as a hung GPU.
 //
 // Region layout (same on every rank; all offsets from the region base):
-//   [0, 1024)            header, local only: seq_send[4], seq_recv[4], arrive[4][16], arrive_all[4], fold_arrive[4], status
-//   [1024, 1280)         data_flag[4][16] u32      written by peers
+//   [0, 1024)            header, local only: seq_send[4], seq_recv[4], arrive_all[4], fold_arrive[4], status
 //   [1280, 1536)         ack_flag[4][16] u32       written by peers
 //   [2048, ...)          slots[depth][world][slot_bytes]
-// slot: [c*k sums f32 | pad to 16 B][c counts i64][c+1 hist i64][max id i64]
+// slot (8-byte LL words): [c*k sums | pad to 16 B][c counts lo,hi][c+1 hist lo,hi][max id lo,hi]
 #include "uem_common.cuh"
 #include <limits.h>
 #include <stddef.h>
@@ -38,25 +43,26 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int kMaxDepth = 4;
 constexpr int kSendChunks = 6;
-constexpr int kOffFlags = 1024, kOffAcks = 1280, kOffSlots = 2048;
+constexpr int kOffAcks = 1280, kOffSlots = 2048;
 constexpr unsigned long long kSpinLimitNs = 2000000000ull;
 
 struct XHeader {
     unsigned seq_send[kMaxDepth];
     unsigned seq_recv[kMaxDepth];
-    unsigned arrive[kMaxDepth][kMaxWorld];
     unsigned arrive_all[kMaxDepth];
     unsigned fold_arrive[kMaxDepth];
     int status;
 };
-static_assert(sizeof(XHeader) <= kOffFlags, "header overflows its page");
+static_assert(sizeof(XHeader) <= kOffAcks, "header overflows its page");
 
 struct Peers {
     char* base[kMaxWorld];
 };
 
-__host__ __device__ inline int64_t sums_bytes(int c, int k) { return (((int64_t)c * k * 4) + 15) & ~(int64_t)15; }
-__host__ __device__ inline int64_t slot_bytes(int c, int k) { return (sums_bytes(c, k) + (int64_t)(2 * c + 2) * 8 + 127) & ~(int64_t)127; }
+// slot geometry in 8-byte LL words
+__host__ __device__ inline int64_t sum_words(int c, int k) { return (((int64_t)c * k) + 3) & ~(int64_t)3; }
+__host__ __device__ inline int64_t tail_words(int c) { return (int64_t)(2 * c + 2) * 2; }   // int64 values as (lo, hi)
+__host__ __device__ inline int64_t slot_bytes(int c, int k) { return ((sum_words(c, k) + tail_words(c)) * 8 + 127) & ~(int64_t)127; }
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
@@ -81,11 +87,33 @@ __device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned want) 
     }
     return true;
 }
+// LL word: one 8-byte transaction {payload, sequence number}
+__device__ __forceinline__ void ll_store(char* dst, unsigned payload, unsigned seq) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(payload), "r"(seq) : "memory");
+}
+// polls (bounded) until the word carries `seq`; *ok = false on timeout
+__device__ __forceinline__ unsigned ll_load(const char* src, unsigned seq, bool* ok) {
+    unsigned v, f;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
+    if (f == seq) return v;
+    const unsigned long long t0 = globaltimer_ns();
+    do {
+        __nanosleep(32);
+        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
+        if (globaltimer_ns() - t0 > kSpinLimitNs) { *ok = false; return v; }
+    } while (f != seq);
+    return v;
+}
+
+__device__ __forceinline__ int64_t ll_load_i64(const char* src, unsigned seq, bool* ok) {
+    const unsigned lo = ll_load(src, seq, ok), hi = ll_load(src + 8, seq, ok);
+    return (int64_t)(((uint64_t)hi << 32) | lo);
+}
 
 __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial, int b,
                                                         int c, int k, const int64_t* __restrict__ max_id,
                                                         const int64_t* __restrict__ hist, const Peers peers, int rank, int world,
-                                                        int slot) {
+                                                        int slot, int64_t* __restrict__ global_id_out) {
     const int ch = blockIdx.x, p = blockIdx.y;
     char* const mine = peers.base[rank];
     XHeader* hdr = reinterpret_cast<XHeader*>(mine);
@@ -102,7 +130,7 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
     const int ck = c * k;
     const int64_t sb = slot_bytes(c, k);
     char* dst = peers.base[p] + kOffSlots + ((int64_t)slot * world + rank) * sb;
-    // chunk ch of the sums, in units of 4 floats; per-image partials folded in image order (the same fp32 additions as
+    // chunk ch of the sums, 4 floats at a time; per-image partials folded in image order (the same fp32 additions as
     // proto_fold_kernel / proto_fold_finalize_kernel: a one-rank exchange reproduces the single-GPU step bit for bit)
     const int nvec = (ck + 3) / 4;
     const int v0 = (int)((int64_t)nvec * ch / gridDim.x), v1 = (int)((int64_t)nvec * (ch + 1) / gridDim.x);
@@ -119,10 +147,11 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
                 for (int u = 0; u < 4; ++u)
                     if (4 * v + u < ck) s[u] += partial[(int64_t)bi * ck + 4 * v + u];
         }
-        *reinterpret_cast<float4*>(dst + (int64_t)v * 16) = make_float4(s[0], s[1], s[2], s[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ll_store(dst + ((int64_t)4 * v + u) * 8, __float_as_uint(s[u]), my);
     }
     if (ch == 0 && threadIdx.x < 2 * c + 2) {
-        int64_t* tail = reinterpret_cast<int64_t*>(dst + sums_bytes(c, k));
+        char* tail = dst + sum_words(c, k) * 8;
         const int i = threadIdx.x;
         int64_t v;
         if (i < c) {
@@ -133,22 +162,36 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
         } else {
             v = max_id ? max_id[0] : -1;
         }
-        tail[i] = v;
+        ll_store(tail + (int64_t)i * 16, (unsigned)((uint64_t)v & 0xffffffffu), my);
+        ll_store(tail + (int64_t)i * 16 + 8, (unsigned)((uint64_t)v >> 32), my);
     }
-    __threadfence_system();
+    // optional: the CTA that fills this rank's own slot also polls the other ranks' max ids of the same step and leaves
+    // the batch-global id (alignment.py:241) for the refine kernel of the NEXT graph -- no separate wait launch
+    if (global_id_out && ch == 0 && p == rank && threadIdx.x < 32) {
+        const int r = threadIdx.x;
+        long long id = LLONG_MIN;
+        if (r < world) {
+            const char* src = mine + kOffSlots + ((int64_t)slot * world + r) * sb + sum_words(c, k) * 8 + (int64_t)(2 * c + 1) * 16;
+            bool ok = true;
+            id = ll_load_i64(src, my, &ok);
+            if (!ok) atomicOr(&hdr->status, 8);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long other = __shfl_xor_sync(0xffffffffu, id, o);
+            id = other > id ? other : id;
+        }
+        if (r == 0) global_id_out[0] = id;
+    }
+    // the last CTA of the launch advances the local sequence number (every CTA has read it by then)
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned old = atomicAdd(&hdr->arrive[slot][p], 1u);
-        if (old == gridDim.x - 1) {   // every chunk of peer p's copy is on its way: publish
-            __threadfence_system();
-            st_release_sys(reinterpret_cast<unsigned*>(peers.base[p] + kOffFlags) + slot * kMaxWorld + rank, my);
-            hdr->arrive[slot][p] = 0u;
-            const unsigned old2 = atomicAdd(&hdr->arrive_all[slot], 1u);
-            if (old2 == (unsigned)world - 1u) {   // the last CTA of the launch: nobody reads seq_send any more
-                hdr->arrive_all[slot] = 0u;
-                __threadfence();
-                *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) = my;
-            }
+        __threadfence();
+        const unsigned old = atomicAdd(&hdr->arrive_all[slot], 1u);
+        if (old == gridDim.x * gridDim.y - 1) {
+            hdr->arrive_all[slot] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) = my;
         }
     }
 }
@@ -160,11 +203,11 @@ __global__ void __launch_bounds__(32) xchg_wait_maxid_kernel(char* __restrict__ 
     const int r = threadIdx.x;
     long long id = LLONG_MIN;
     if (r < world) {
-        const unsigned* flag = reinterpret_cast<const unsigned*>(region + kOffFlags) + slot * kMaxWorld + r;
-        if (!spin_until(flag, want)) atomicOr(&hdr->status, 8);
         const int64_t sb = slot_bytes(c, k);
-        const char* src = region + kOffSlots + ((int64_t)slot * world + r) * sb + sums_bytes(c, k);
-        id = *reinterpret_cast<const volatile long long*>(src + (int64_t)(2 * c + 1) * 8);
+        const char* src = region + kOffSlots + ((int64_t)slot * world + r) * sb + sum_words(c, k) * 8 + (int64_t)(2 * c + 1) * 16;
+        bool ok = true;
+        id = ll_load_i64(src, want, &ok);
+        if (!ok) atomicOr(&hdr->status, 8);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -181,22 +224,20 @@ __global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers pee
     char* const region = peers.base[rank];
     XHeader* hdr = reinterpret_cast<XHeader*>(region);
     const unsigned want = *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) + 1u;
-    if (threadIdx.x < world) {   // uem_xchg_wait_maxid must have run before on this stream: verify, never spin here
-        const unsigned* flag = reinterpret_cast<const unsigned*>(region + kOffFlags) + slot * kMaxWorld + threadIdx.x;
-        if ((int)(ld_acquire_sys(flag) - want) < 0) atomicOr(&hdr->status, 16);
-    }
-    __syncthreads();
     const int ck = c * k;
     const int64_t sb = slot_bytes(c, k);
     const char* slots = region + kOffSlots + (int64_t)slot * world * sb;
+    const char* tails = slots + sum_words(c, k) * 8;
     const int i = blockIdx.x * 256 + threadIdx.x;
+    bool ok = true;
     if (i < ck) {
         const int ci = i / k;
-        float s = *reinterpret_cast<const float*>(slots + (int64_t)i * 4);
-        int64_t n = *reinterpret_cast<const int64_t*>(slots + sums_bytes(c, k) + (int64_t)ci * 8);
-        for (int r = 1; r < world; ++r) {   // rank order: identical on every rank
-            s += *reinterpret_cast<const float*>(slots + r * sb + (int64_t)i * 4);
-            n += *reinterpret_cast<const int64_t*>(slots + r * sb + sums_bytes(c, k) + (int64_t)ci * 8);
+        float s = 0.f;
+        int64_t n = 0;
+        for (int r = 0; r < world; ++r) {   // rank order: identical on every rank
+            const float v = __uint_as_float(ll_load(slots + r * sb + (int64_t)i * 8, want, &ok));
+            s = r ? s + v : v;
+            n += ll_load_i64(tails + r * sb + (int64_t)ci * 16, want, &ok);
         }
         if (sums_out) sums_out[i] = s;
         if (proto_new) {
@@ -208,10 +249,11 @@ __global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers pee
     }
     if (i < 2 * c + 1 && (counts_out || hist_out)) {
         int64_t n = 0;
-        for (int r = 0; r < world; ++r) n += *reinterpret_cast<const int64_t*>(slots + r * sb + sums_bytes(c, k) + (int64_t)i * 8);
+        for (int r = 0; r < world; ++r) n += ll_load_i64(tails + r * sb + (int64_t)i * 16, want, &ok);
         if (i < c) { if (counts_out) counts_out[i] = n; }
         else if (hist_out) hist_out[i - c] = n;
     }
+    if (!ok) atomicOr(&hdr->status, 8);
     // the last CTA acknowledges the slot to every peer and advances the local sequence number
     __threadfence();
     __syncthreads();
@@ -247,14 +289,15 @@ extern "C" int64_t uem_xchg_region_bytes(int world, int depth, int c, int k) {
 }
 
 extern "C" int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
-                                 const void* const* peer_regions, int rank, int world, int depth, int slot, void* stream) {
+                                 const void* const* peer_regions, int rank, int world, int depth, int slot, int64_t* global_id_out,
+                                 void* stream) {
     UEM_REQUIRE(partials_ws && b > 0 && c > 0 && c <= UEM_MAX_C && k > 0, "uem_xchg_send_f32: bad arguments");
     Peers P;
     if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_send_f32")) return rc;
     const float* partial = (const float*)partials_ws;
     const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
     xchg_send_kernel<<<dim3(kSendChunks, world), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, max_id, hist, P, rank, world,
-                                                                                slot);
+                                                                                slot, global_id_out);
     UEM_CHECK_LAUNCH();
     return 0;
 }

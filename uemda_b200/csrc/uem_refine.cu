@@ -768,7 +768,9 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
     // shared memory: [warp][stage][C planes x WC floats | WC ids]  [warp][3C][32 lanes] float2 D state  [warp][2][ncols_max][TS] taps
     unsigned char* const wstage = smem_col + (size_t)wid * NS * kWarpStage;
     const uint32_t dstate = smem_u32(smem_col + (size_t)NW * NS * kWarpStage + (size_t)wid * kWarpD) + (uint32_t)lane * 8u;
-    float* const taps = reinterpret_cast<float*>(smem_col + (size_t)NW * NS * kWarpStage + (size_t)NW * kWarpD) + (size_t)wid * 2 * ncols_max * TS;
+    // two tap buffers per warp: the taps of the NEXT low-res row pair are prefetched (cp.async) while this one is in use
+    float* const taps_base = reinterpret_cast<float*>(smem_col + (size_t)NW * NS * kWarpStage + (size_t)NW * kWarpD) + (size_t)wid * 4 * ncols_max * TS;
+    const int tap_buf_floats = 2 * ncols_max * TS;
 
     const int64_t total = (int64_t)p.b * nstrips * H;
     const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
@@ -899,6 +901,29 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
         tb = reinterpret_cast<const float4*>(p.sw + (int64_t)bi * (p.R + 1) * CP);
     };
 
+    // ---- low-res taps.  The warp's 64 columns span `ncols` low-res columns; their 2 rows x ncols x 3C values are copied
+    // (lane -> (map, class), raw) into a tap buffer with 4-byte cp.async.  The copy for the NEXT row pair is issued right
+    // after a setup, ~H/h rows before it is needed, so its L2 / DRAM round trips (two dependent ones when issued on
+    // demand: 8% of all warp stall samples in profiles/r02_ncu_refine_col2.txt) disappear behind the row loop.
+    auto tap_fetch_async = [&](float* buf, int bsu, int i0u, int i1u) {
+        if (lane >= 3 * C) return;
+        const int bi = bsu / nstrips, su = bsu - bi * nstrips;
+        const int xw = su * NT * 2 + wid * WC;
+        const int ab = make_lerp(min(xw, W - 1), w, p.sx).i0;
+        const int nc = make_lerp(min(xw + WC - 1, W - 1), w, p.sx).i1 - ab + 1;
+        const int m = lane / C, ci = lane - m * C;
+        const float* plane = p.maps[m] + ((int64_t)bi * C + ci) * hw_low + ab;
+        const float* r0 = plane + i0u * w;
+        const float* r1 = plane + i1u * w;
+        float* dst = buf + m * CP + ci;
+        for (int j = 0; j < nc; ++j) {
+            cp_async_4(dst + j * TS, r0 + j);
+            cp_async_4(dst + (ncols_max + j) * TS, r1 + j);
+        }
+    };
+    int tap_cur = 0;                  // buffer the current column state was built from
+    int pref_bs = -1, pref_i0 = -1, pref_it = 0;   // what the other buffer holds (or will hold), and when it was issued
+
     int bs = bs0, y = y0;
     int stage = 0, pstage = NS - 1;
     {   // row 0's gather
@@ -938,32 +963,19 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
             // pre-scaled by log2 e [/temp]; every lane then interpolates its two columns horizontally, once
             cur_i0 = ly.i0;
             __syncwarp();
-            if (lane < 3 * C) {
-                const int m = lane / C, ci = lane - m * C;
-                const float* plane = p.maps[m] + ((int64_t)cur_b * C + ci) * hw_low + abase;
-                const float sc = p.map_scale[m];
-                float* dst = taps + m * CP + ci;
-                const float* r0 = plane + ly.i0 * w;
-                const float* r1 = plane + ly.i1 * w;
-                for (int j0 = 0; j0 < ncols; j0 += 4) {
-                    float u0[4], u1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = min(j0 + u, ncols - 1);
-                        u0[u] = __ldg(r0 + j);
-                        u1[u] = __ldg(r1 + j);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (j0 + u < ncols) {
-                            dst[(j0 + u) * TS] = u0[u] * sc;
-                            dst[(ncols_max + j0 + u) * TS] = u1[u] * sc;
-                        }
-                }
+            if (pref_bs == bs && pref_i0 == ly.i0) {
+                tap_cur ^= 1;                                   // prefetched after the previous setup
+                if (it - pref_it < NS) cp_async_wait_group<0>();   // issued too recently for the row loop's waits to cover it
+            } else {                                            // first setup of this CTA: fetch on demand
+                tap_fetch_async(taps_base + tap_cur * tap_buf_floats, bs, ly.i0, ly.i1);
+                cp_async_commit_group();
+                cp_async_wait_group<0>();
             }
             __syncwarp();
+            const float* taps = taps_base + tap_cur * tap_buf_floats;
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
+                const float sc = p.map_scale[m];   // log2 e [/temp], applied to the raw taps exactly as before the lerp
                 float ta[2][C], td[2][C];
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
@@ -976,8 +988,8 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
                     load_tap<C>(t01 + ncols_max * TS, v11);
 #pragma unroll
                     for (int ci = 0; ci < C; ++ci) {   // the rounded operations of refine_col_kernel, per component
-                        const float a = __fmaf_rn(l1x[v], v01[ci], __fmul_rn(l0x[v], v00[ci]));
-                        const float bq = __fmaf_rn(l1x[v], v11[ci], __fmul_rn(l0x[v], v10[ci]));
+                        const float a = __fmaf_rn(l1x[v], __fmul_rn(v01[ci], sc), __fmul_rn(l0x[v], __fmul_rn(v00[ci], sc)));
+                        const float bq = __fmaf_rn(l1x[v], __fmul_rn(v11[ci], sc), __fmul_rn(l0x[v], __fmul_rn(v10[ci], sc)));
                         ta[v][ci] = a;
                         td[v][ci] = __fadd_rn(bq, -a);
                     }
@@ -990,6 +1002,19 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
                     } else {
                         Dr[DSM ? 0 : m][DSM ? 0 : ci] = make_float2(td[0][ci], td[1][ci]);
                     }
+                }
+            }
+            {   // where is the next setup?  the first later row of this unit with another low-res row pair, or the next unit
+                int yn = y + 1;
+                while (yn < H && make_lerp(yn, h, p.sy).i0 == ly.i0) ++yn;
+                const int it_n = it + (yn - y);
+                pref_bs = -1;
+                if (it_n < n) {
+                    const int nbs = yn < H ? bs : bs + 1;
+                    const Lerp ln = make_lerp(yn < H ? yn : 0, h, p.sy);
+                    __syncwarp();   // every lane has read its taps of the buffer that is overwritten now (two setups ago)
+                    tap_fetch_async(taps_base + (tap_cur ^ 1) * tap_buf_floats, nbs, ln.i0, ln.i1);
+                    pref_bs = nbs; pref_i0 = ln.i0; pref_it = it;
                 }
             }
         }
@@ -1220,13 +1245,14 @@ static int launch_refine_col2(RefineParams p, cudaStream_t st, bool pdl, bool* d
     int ncols_max = (int)(63 * p.sx) + 3;   // low-res columns a warp's 64 image columns can span (+1 for the right neighbour)
     if (ncols_max > p.w) ncols_max = p.w;
     const size_t smem = (size_t)NS * NT * 2 * (4 * C + 8) + (DSM ? (size_t)NT * 3 * C * 8 : 0) +
-                        (size_t)(NT / 32) * 2 * ncols_max * 3 * cp_of(C) * 4;
+                        (size_t)(NT / 32) * 4 * ncols_max * 3 * cp_of(C) * 4;   // stages | D state | 2 tap buffers per warp
     if (smem > 100 * 1024 || (int64_t)p.H * p.W >= ((int64_t)1 << 31)) return 0;   // the first form / generic kernels take it
     auto kernel = refine_col2_kernel<C, NT, NS, DSM, MINB>;
     if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
     if (per_sm < 1) per_sm = 1;
+    if (g_uem_refine_ctas_per_sm > 0 && per_sm > g_uem_refine_ctas_per_sm) per_sm = g_uem_refine_ctas_per_sm;
     const int nstrips = (p.W + NT * 2 - 1) / (NT * 2);
     const int64_t total = (int64_t)p.b * nstrips * p.H;
     const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
@@ -1275,6 +1301,7 @@ static int launch_refine_col(RefineParams p, cudaStream_t st, bool pdl, bool* do
     int per_sm = 0;
     UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
     if (per_sm < 1) per_sm = 1;
+    if (g_uem_refine_ctas_per_sm > 0 && per_sm > g_uem_refine_ctas_per_sm) per_sm = g_uem_refine_ctas_per_sm;
     const int nstrips = (p.W + NT * VX - 1) / (NT * VX);
     const int64_t total = (int64_t)p.b * nstrips * p.H;
     const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
@@ -1364,6 +1391,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
 
 extern "C" int uem_set_option(const char* name, int value) {
     UEM_REQUIRE(name, "uem_set_option: NULL name");
+    if (strcmp(name, "refine_ctas_per_sm") == 0) { g_uem_refine_ctas_per_sm = value; return 0; }
+    if (strcmp(name, "region_ctas_per_sm") == 0) { g_uem_region_ctas_per_sm = value; return 0; }
     if (strcmp(name, "refine_form") == 0) { g_refine_form = value < 0 ? -1 : (value ? 1 : 0); return 0; }   // -1: back to the default
     return uem_fail("uem_set_option: unknown option '%s'", name);
 }

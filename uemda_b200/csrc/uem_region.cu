@@ -644,7 +644,8 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
     // the kernel is compiled for <= 64 registers (1024 threads per SM): two CTAs of 512 threads per SM when two private
     // tables fit, otherwise a single 1024-thread CTA; one wave
     const int threads = (2 * (smem + 1024) <= 220 * 1024) ? 512 : 1024;
-    const int per_sm = threads == 512 ? 2 : 1;
+    int per_sm = threads == 512 ? 2 : 1;
+    if (g_uem_region_ctas_per_sm > 0 && per_sm > g_uem_region_ctas_per_sm) per_sm = g_uem_region_ctas_per_sm;
     int chunks = max(1, (UEM_SMS * per_sm) / b);
     const int64_t groups = N / (vec ? 4 : 1);
     chunks = (int)min((int64_t)chunks, max((int64_t)1, groups / threads));

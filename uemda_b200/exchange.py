@@ -3,8 +3,8 @@
 One process per GPU; every rank owns a *symmetric region* (csrc/uem_exchange.cu for the layout) that all peers map into
 their own address space.  A step's statistics -- prototype partial sums + counts (alignment.py:347-353), the class
 histogram (balance.py:45-52) and the rank-local max superpixel id (alignment.py:241) -- are stored straight into every
-peer's region by ``send`` (NVLink peer stores + a release flag), acquired by ``wait_max_id`` and folded in rank order by
-``fold_finalize``; all three are plain kernel launches on the caller's stream, so a sharded step is captured in CUDA
+peer's region by ``send`` (NVLink peer stores, every word paired with a sequence number), polled by ``wait_max_id`` and
+folded in rank order by ``fold_finalize``; all three are plain kernel launches on the caller's stream, so a sharded step is captured in CUDA
 graphs with no host-issued collective in between.  The NCCL form (``ShardedMiner.exchange``: one all_gather) stays as the
 fallback and as the reference the tests compare this one with.
 
@@ -123,15 +123,17 @@ class PeerExchange:
         return [cls(ptrs, r, world, c, k, depth, device, keep=regions, backend="local") for r in range(world)]
 
     # ------------------------------------------------------------------ the three launches (capturable)
-    def send(self, partials, max_id, slot, hist=None):
+    def send(self, partials, max_id, slot, hist=None, global_id_out=None):
         """partials: ``ops.proto_accumulate(..., fold=False)`` of this rank's source shard; max_id: (1,) int64 rank-local
-        max superpixel id (or None); hist: (c+1,) int64 class histogram of this rank's labels (or None)."""
+        max superpixel id (or None); hist: (c+1,) int64 class histogram of this rank's labels (or None).
+        global_id_out: optional (1,) int64 tensor; the launch then also polls the other ranks' ids of this step and leaves the
+        batch-global max id there (= ``wait_max_id`` without its own launch)."""
         ws, (b, c, k) = partials
         assert (c, k) == (self.c, self.k)
-        L.require_cuda(ws, max_id, hist)
+        L.require_cuda(ws, max_id, hist, global_id_out)
         lib = L.bind(ws)
         L.check(lib.uem_xchg_send_f32(L.ptr(ws), b, c, k, L.ptr(max_id), L.ptr(hist), self._arr, self.rank, self.world, self.depth,
-                                      int(slot), L.stream_of(ws)))
+                                      int(slot), L.ptr(global_id_out), L.stream_of(ws)))
 
     def wait_max_id(self, slot, out=None):
         """Blocks the current stream until every rank's vector of ``slot`` has arrived -> batch-global max id (1,) int64."""
@@ -165,7 +167,7 @@ class PeerExchange:
         return new, sums, counts, hist
 
     def status(self):
-        """Synchronises the current stream; 0 = fine, bit 8 = a bounded spin timed out, bit 16 = fold before arrival."""
+        """Synchronises the current stream; 0 = fine, bit 8 = a bounded poll timed out (2 s)."""
         out = ctypes.c_int(0)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         L.check(L.load().uem_xchg_status(ctypes.c_void_p(self.ptrs[self.rank]), ctypes.byref(out), stream))
@@ -174,5 +176,5 @@ class PeerExchange:
     def check(self):
         s = self.status()
         if s:
-            raise ExchangeError("exchange status %d: %s" % (s, "a peer's vector / acknowledgement did not arrive within 2 s"
-                                                            if s & 8 else "fold_finalize ran before wait_max_id"))
+            raise ExchangeError("exchange status %d: a peer's vector / acknowledgement did not arrive within 2 s (a rank is gone, "
+                                "or send / wait / fold are not issued in lockstep on every rank)" % s)
