@@ -1116,3 +1116,23 @@ def test_sliding_window_golden(dev):
     from oracle import uem_oracle as O
     views = [torch.rand(1, 4, 16, 16) for _ in range(8)]
     assert_close(T.views_mean([v.to(dev) for v in views]), O.tta_mean(views), rtol=1e-6, atol=1e-7, what="views mean")
+
+
+def test_regeneration_label_histogram(dev):
+    """run_sharded on one rank: the label histogram it returns counts every produced uint8 value exactly once."""
+    from uemda_b200.gast.alignment import Aligner
+    from uemda_b200.regen import PseudoLabelRegenerator
+    from uemda_b200.synth import Workload, make_inputs
+    wl = Workload("regen3", 2, 6, 64, 64, 32, 16, 16)
+    batches, outs = [], []
+    for i in range(3):
+        inp = make_inputs(wl, seed=200 + i, with_source=False)
+        batches.append({"soft": inp["soft"].pin_memory(), "sup": inp["sup"].pin_memory(), "feat": inp["feat"].pin_memory(),
+                        "preds": [inp["pred1"].pin_memory(), inp["pred2"].pin_memory()], "names": None})
+    al = Aligner(_Log(), feat_channels=wl.k, class_num=wl.c, decay=0.996)
+    al.prototypes = inp["prototypes"].to(dev)
+    regen = PseudoLabelRegenerator(al, 0.8, 0.6, mode="all", temp=2.0, num_regions=int(inp["ignore_id"]) + 1)
+    n, hist = regen.run_sharded(batches, lambda names, arr: outs.append(arr.copy()), device=dev)
+    assert n == 6
+    want = np.bincount(np.concatenate([o.reshape(-1) for o in outs]), minlength=wl.c + 1)
+    assert np.array_equal(hist.cpu().numpy(), want)

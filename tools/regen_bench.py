@@ -81,7 +81,7 @@ def main():
     regen.run(batches[:2], lambda names, arr: None, 0, 1, dev)
     barrier()
     e0.record()
-    n_done = regen.run(batches, lambda names, arr: None, rank, world, dev)
+    n_done, hist = regen.run_sharded(batches, lambda names, arr: None, device=dev, class_num=wl.c)
     e1.record()
     barrier()
     t_st = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -95,7 +95,9 @@ def main():
                           "resident_Mpixel_s": px / float(t_res.item()) / 1e3, "resident_ms": float(t_res.item()),
                           "staged_Mpixel_s": px / float(t_st.item()) / 1e3, "staged_ms": float(t_st.item()),
                           "h2d_bytes_per_tile": in_bytes // args.batch, "d2h_bytes_per_tile": wl.H * wl.W,
-                          "tiles_rank0": n_done * 1}))
+                          "tiles_rank0": n_done * 1, "label_hist_global": [int(v) for v in hist.cpu()],
+                          "label_hist_total_ok": int(hist.sum()) == px,
+                          "efficiency_note": "weak-scaling denominator: the same command at 1 GPU"}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -35,6 +35,7 @@ class PseudoLabelRegenerator:
         self.refine = refine and aligner is not None
         self.num_regions = num_regions
         self._ws = None
+        self.label_hist = None   # set by run_sharded: (c+1,) int64 counts of the produced uint8 values
 
     # ------------------------------------------------------------------ one batch, device tensors in, uint8 out
     def _chain(self, soft, sup, feat, preds):
@@ -60,8 +61,22 @@ class PseudoLabelRegenerator:
             self._ws = (key, torch.zeros(int(need), dtype=torch.uint8, device=soft.device))
         return self._ws[1]
 
+    def _count(self, u8):
+        """running histogram of the produced maps over uint8 values 0 (ignored) .. c (class c-1), on the device"""
+        if self.label_hist is None:
+            return u8
+        c = self.label_hist.numel() - 1
+        # class_hist counts labels in [0, c) and, last, the non-ignored ones: feed it label - 1 with ignore = -1
+        h = ops.class_hist(u8.to(torch.int64) - 1, c, -1)
+        self.label_hist[1:] += h[:-1]
+        self.label_hist[0] += u8.numel() - h[-1]
+        return u8
+
     def process(self, soft, sup=None, feat=None, preds=None):
         """soft (b,c,H,W) probabilities [+ sup (b,1,H,W) int64, feat (b,k,h,w), preds] -> (b,H,W) uint8 = label + 1."""
+        return self._count(self._process(soft, sup, feat, preds))
+
+    def _process(self, soft, sup=None, feat=None, preds=None):
         L.require_cuda(soft, sup, feat)
         if not self.refine:
             from .gast.pseudo_generation import pseudo_selection
@@ -142,3 +157,34 @@ class PseudoLabelRegenerator:
                 sink(names, host.numpy())
             staged = nxt
         return done
+
+    # ------------------------------------------------------------------ the tile list sharded over the ranks of a job
+    def run_sharded(self, batches, sink, group=None, device=None, class_num=None):
+        """BASELINE config 4: the tile list sharded over the ranks of a torch.distributed job (one process per GPU,
+        contiguous slices, no data-path collective).  Before the loop the prototype bank is broadcast from rank 0 and
+        checked to be bit-identical everywhere (every rank refines against the same bank, as the un-sharded reference does);
+        after it the class histogram of the produced label maps (uint8 values 0 = ignored, 1..c) is all-reduced, so every
+        rank holds the label statistics of the WHOLE regenerated set (what ClassBalance / the IAST thresholds of the next
+        self-training round start from).  Returns (tiles processed by this rank, global histogram (c+1,) int64)."""
+        import torch.distributed as dist
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        c = class_num or (self.aligner.class_num if self.aligner is not None else None)
+        assert c is not None, "class_num is needed for the label histogram"
+        if world > 1 and self.aligner is not None:
+            bank = self.aligner.prototypes.contiguous()
+            dist.broadcast(bank, 0, group=group)
+            self.aligner.prototypes = bank
+            chk = torch.stack([bank.double().sum(), bank.double().abs().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            assert torch.equal(lo, hi), "prototype bank differs across ranks after the broadcast"
+        self.label_hist = torch.zeros(c + 1, dtype=torch.int64, device=device)
+        done = self.run(batches, sink, rank=rank, world_size=world, device=device)
+        hist = self.label_hist
+        self.label_hist = None
+        if world > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        return done, hist
