@@ -339,12 +339,15 @@ UEM_API int uem_peer_free(void* ptr);
  * forward : sums[m] += sum_px coef * CrossEntropy(upsample(x_m))[px, target]   (fp64, zeroed by the caller); the loss
  *           is (sums[0] [+ sums[1]]) / (valid + 1e-7) / heads.
  * backward: g_m (b,c,h,w) = scale[0] * d sums[m] / d x_m, every element written, deterministic (a gather per low-res
- *           cell, no atomics); scale: device scalar = grad_out / (valid + 1e-7) / heads. */
+ *           cell, no atomics); scale: device scalar = grad_out / (valid + 1e-7) / heads.  ws: uem_uvem_loss_backward_ws_bytes
+ *           bytes of scratch -> every pixel's softmax is evaluated once (per-block partials, then a fixed-order gather per
+ *           cell); NULL -> the one-warp-per-cell form without scratch (4x the exponentials). */
 UEM_API int uem_uvem_loss_forward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
                               const int64_t* target, const float* coef, double* sums, void* stream);
+UEM_API int64_t uem_uvem_loss_backward_ws_bytes(int b, int c, int h, int w, int heads);
 UEM_API int uem_uvem_loss_backward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
                                const int64_t* target, const float* coef, const float* scale, float* g1, float* g2,
-                               void* stream);
+                               void* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1136,3 +1136,27 @@ def test_regeneration_label_histogram(dev):
     assert n == 6
     want = np.bincount(np.concatenate([o.reshape(-1) for o in outs]), minlength=wl.c + 1)
     assert np.array_equal(hist.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 8, 8, 128, 128), (1, 7, 5, 9, 37, 50), (2, 3, 4, 4, 4, 4), (1, 8, 3, 5, 48, 80), (8, 6, 32, 32, 512, 512)])
+@pytest.mark.parametrize("heads", [1, 2])
+def test_uvem_loss_backward_forms_agree(dev, shape, heads):
+    """The two forms of the fused UVEM-loss backward (per-block partials + gather: every softmax once; one warp per low-res
+    cell: the round-1 kernel) give the same gradient up to fp32 summation order, each of them bit-reproducibly."""
+    from uemda_b200 import ops
+    b, c, h, w, H, W = shape
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x1 = (torch.randn(b, c, h, w, generator=g) * 3).to(dev)
+    x2 = (torch.randn(b, c, h, w, generator=g) * 3).to(dev) if heads == 2 else None
+    target = torch.randint(-1, c, (b, H, W), generator=g).to(dev)
+    coef = torch.rand(b * H * W, generator=g).to(dev)
+    coef[target.reshape(-1) < 0] = 0.0
+    coef[torch.rand(b * H * W, generator=g).to(dev) < 0.3] = 0.0
+    scale = torch.tensor([0.37], device=dev)
+    a = ops.uvem_loss_backward(x1, x2, target, coef, scale)
+    a2 = ops.uvem_loss_backward(x1, x2, target, coef, scale)
+    r = ops.uvem_loss_backward(x1, x2, target, coef, scale, per_cell=True)
+    for m in range(heads):
+        assert torch.equal(a[m], a2[m]), "backward is not bit-reproducible"
+        tol = 1e-5 * float(r[m].abs().max())
+        assert_close(a[m], r[m], rtol=1e-4, atol=tol, what="backward forms, head %d" % m)

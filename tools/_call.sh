@@ -1,9 +1,2 @@
-export NCCL_DEBUG=WARN
-for N in 4 8; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 40 --warmup 10 > gpurun_out/r2_bench_${N}gpu_c.json 2> gpurun_out/r2_bench_${N}gpu_c.err
-echo "${N}gpu rc=$?" >> gpurun_out/r2_scale.txt; tail -c 300 gpurun_out/r2_bench_${N}gpu_c.err | tr '\n' ' ' >> gpurun_out/r2_scale.txt
-python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/r2_bench_${N}gpu_c.json') if l.startswith('{')][-1]); print('${N}gpu', round(d['value']), round(d['ms_per_step']*1e3,1), d['impl_detail']['exchange'], d['impl_detail']['exchange_status'], d['kernels_per_step'], 'e2e', round(d['e2e']['value']), json.dumps(d.get('parity'))[:330])" >> gpurun_out/r2_scale.txt
-done
-cat gpurun_out/r2_scale.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r2_pytest6.log; tail -c 700 gpurun_out/r2_pytest6.log
+python tools/lossbench.py > gpurun_out/r2_lossbench.txt 2>&1; cat gpurun_out/r2_lossbench.txt

@@ -91,7 +91,8 @@ SIGNATURES = {
     "uem_peer_close": (_I, [_P]),
     "uem_peer_free": (_I, [_P]),
     "uem_uvem_loss_forward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "uem_uvem_loss_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "uem_uvem_loss_backward_ws_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "uem_uvem_loss_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

@@ -257,7 +257,145 @@ __global__ void __launch_bounds__(32) uvem_ce_grad_kernel(const float* __restric
         }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, second form (round 2, the default): every pixel's softmax is evaluated ONCE.
+// The full-resolution image splits into h x w "blocks": block (qi, qj) = the pixels whose interpolation starts at low-res
+// (qi, qj), i.e. that interpolate from the 2x2 corner cells (qi | qi+1, qj | qj+1).  Pass 1: one warp per block keeps the
+// four corners' logits in registers, walks its ~H/h x W/w pixels, and accumulates for the 4 corners x heads x classes
+// w_y * w_x * coef * (p_c - [c == target]) in per-lane registers; one warp reduction, then 4 * NM * C plain stores into a
+// per-block partial table.  Pass 2: every low-res cell adds the (at most 4 blocks x corners) partials that point at it,
+// in a fixed order.  No atomics anywhere: the gradient is bit-reproducible run to run; 4x fewer exponentials than the
+// per-cell gather above (149 us -> see profiles/r02_lossbench.txt), which stays for the A/B comparison.
+// ------------------------------------------------------------------------------------------------
+template <int C, int NM>
+__global__ void __launch_bounds__(128) uvem_ce_grad_block_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int b, int h,
+                                                                 int w, int H, int W, float sy, float sx,
+                                                                 const int64_t* __restrict__ target, const float* __restrict__ coef,
+                                                                 float* __restrict__ part) {
+    constexpr float kL2E = 1.4426950408889634f;
+    const int lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int64_t nblk = (int64_t)b * h * w;
+    if (blk >= nblk) return;
+    const int qj = (int)(blk % w), qi = (int)((blk / w) % h), bi = (int)(blk / ((int64_t)w * h));
+    const int hw_low = h * w;
+    const int64_t HW = (int64_t)H * W;
+    const float* maps[2] = {x1, x2};
+    const int y0 = first_with_i0_ge(qi, h, H, sy), y1 = first_with_i0_ge(qi + 1, h, H, sy);
+    const int x0 = first_with_i0_ge(qj, w, W, sx), x1e = first_with_i0_ge(qj + 1, w, W, sx);
+    const int qi1 = min(qi + 1, h - 1), qj1 = min(qj + 1, w - 1);
+    float nb[NM][C][2][2];   // the block's corner logits, pre-scaled by log2 e
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const float* pl = maps[m] + ((int64_t)bi * C + ci) * hw_low;
+            nb[m][ci][0][0] = __ldg(pl + qi * w + qj) * kL2E;
+            nb[m][ci][0][1] = __ldg(pl + qi * w + qj1) * kL2E;
+            nb[m][ci][1][0] = __ldg(pl + qi1 * w + qj) * kL2E;
+            nb[m][ci][1][1] = __ldg(pl + qi1 * w + qj1) * kL2E;
+        }
+    float acc[2][2][NM][C];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) acc[dy][dx][m][ci] = 0.f;
+    const int fw = x1e - x0, fh = y1 - y0;
+    if (fw > 0 && fh > 0) {
+        const int npx = fw * fh;
+        int fy = 0, fx = lane;
+        while (fx >= fw) { fx -= fw; ++fy; }
+        for (int q = lane; q < npx; q += 32) {
+            const int y = y0 + fy, x = x0 + fx;
+            const int64_t px = (int64_t)bi * HW + (int64_t)y * W + x;
+            const float cf = __ldg(coef + px);
+            if (cf != 0.f) {
+                const Lerp ly = make_lerp(y, h, sy), lx = make_lerp(x, w, sx);
+                const int t = (int)__ldg(target + px);
+                const float w00 = ly.l0 * lx.l0 * cf, w01 = ly.l0 * lx.l1 * cf, w10 = ly.l1 * lx.l0 * cf, w11 = ly.l1 * lx.l1 * cf;
+#pragma unroll
+                for (int m = 0; m < NM; ++m) {
+                    float z[C];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) {   // the forward's interpolation, operation by operation
+                        z[ci] = ly.l0 * (lx.l0 * nb[m][ci][0][0] + lx.l1 * nb[m][ci][0][1]) +
+                                ly.l1 * (lx.l0 * nb[m][ci][1][0] + lx.l1 * nb[m][ci][1][1]);
+                        mx = fmaxf(mx, z[ci]);
+                    }
+                    float S = 0.f;
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) { z[ci] = ex2_approx(z[ci] - mx); S += z[ci]; }
+                    float r = rcp_approx(S);
+                    r = fmaf(r, fmaf(-S, r, 1.0f), r);
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) {
+                        const float g = fmaf(z[ci], r, (t == ci) ? -1.0f : 0.0f);   // p_c - [c == target]
+                        acc[0][0][m][ci] = fmaf(w00, g, acc[0][0][m][ci]);
+                        acc[0][1][m][ci] = fmaf(w01, g, acc[0][1][m][ci]);
+                        acc[1][0][m][ci] = fmaf(w10, g, acc[1][0][m][ci]);
+                        acc[1][1][m][ci] = fmaf(w11, g, acc[1][1][m][ci]);
+                    }
+                }
+            }
+            fx += 32;
+            while (fx >= fw) { fx -= fw; ++fy; }
+        }
+    }
+    float* dst = part + blk * (4 * NM * C);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+            for (int m = 0; m < NM; ++m)
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float v = warp_sum(acc[dy][dx][m][ci]);
+                    if (lane == 0) dst[((dy * 2 + dx) * NM + m) * C + ci] = v;
+                }
+}
+
+// Pass 2: cell (i, j) of head m, class ci <- the partials of the blocks qi in {i-1, i}, qj in {j-1, j} whose corner
+// (dy, dx) lands on it (min(qi + dy, h-1) == i: the clamped last row / column receives two corners of its own block)
+template <int C, int NM>
+__global__ void __launch_bounds__(256) uvem_ce_grad_gather_kernel(const float* __restrict__ part, int b, int h, int w,
+                                                                  const float* __restrict__ scale, float* __restrict__ g1,
+                                                                  float* __restrict__ g2) {
+    const int64_t total = (int64_t)b * NM * C * h * w;
+    const float sc = __ldg(scale);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % w), i = (int)((e / w) % h);
+        const int ci = (int)((e / ((int64_t)w * h)) % C), m = (int)((e / ((int64_t)w * h * C)) % NM);
+        const int bi = (int)(e / ((int64_t)w * h * C * NM));
+        float s = 0.f;
+#pragma unroll
+        for (int oy = 1; oy >= 0; --oy)        // blocks in the order (i-1, j-1), (i-1, j), (i, j-1), (i, j)
+#pragma unroll
+            for (int ox = 1; ox >= 0; --ox) {
+                const int qi = i - oy, qj = j - ox;
+                if (qi < 0 || qj < 0) continue;
+                const float* src = part + (((int64_t)bi * h + qi) * w + qj) * (4 * NM * C);
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx)
+                        if (min(qi + dy, h - 1) == i && min(qj + dx, w - 1) == j) s += src[((dy * 2 + dx) * NM + m) * C + ci];
+            }
+        float* g = m == 0 ? g1 : g2;
+        g[((int64_t)bi * C + ci) * h * w + (int64_t)i * w + j] = s * sc;
+    }
+}
+
 }  // namespace
+
+extern "C" int64_t uem_uvem_loss_backward_ws_bytes(int b, int c, int h, int w, int heads) {
+    return (int64_t)b * h * w * 4 * heads * c * 4;
+}
 
 // sums: nheads fp64 accumulators, zeroed by the caller.  sum_m = sum_px coef * CE(up(x_m))[target]
 extern "C" int uem_uvem_loss_forward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
@@ -301,15 +439,33 @@ extern "C" int uem_uvem_loss_forward_f32(const float* x1, const float* x2, int b
 }
 
 // g_m (b,c,h,w) = scale[0] * d/dx_m sum_px coef * CE(up(x_m))[target]; every element is written (no zero-init needed)
+// ws: uem_uvem_loss_backward_ws_bytes(b, c, h, w, heads) bytes of scratch (the per-block partials), or NULL for the
+// first form (one warp per low-res cell; 4x the exponentials, no scratch)
 extern "C" int uem_uvem_loss_backward_f32(const float* x1, const float* x2, int b, int c, int h, int w, int H, int W,
                                           const int64_t* target, const float* coef, const float* scale, float* g1, float* g2,
-                                          void* stream) {
+                                          void* ws, void* stream) {
     UEM_REQUIRE(x1 && g1 && target && coef && scale && b > 0 && h > 0 && w > 0 && H > 0 && W > 0,
                 "uem_uvem_loss_backward_f32: bad arguments");
     UEM_REQUIRE(!x2 == !g2, "uem_uvem_loss_backward_f32: second head needs its gradient buffer");
     UEM_REQUIRE(h <= 65535 && b <= 65535, "uem_uvem_loss_backward_f32: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     const float sy = uem_align_corners_scale(h, H), sx = uem_align_corners_scale(w, W);
+    if (ws) {
+        const int64_t nblk = (int64_t)b * h * w;
+        const int64_t elems = nblk * c * (x2 ? 2 : 1);
+        const int ggrid = (int)min((int64_t)UEM_SMS * 8, (elems + 255) / 256);
+        UEM_DISPATCH_C(c, {
+            if (x2) {
+                uvem_ce_grad_block_kernel<C, 2><<<(unsigned)((nblk + 3) / 4), 128, 0, st>>>(x1, x2, b, h, w, H, W, sy, sx, target, coef, (float*)ws);
+                uvem_ce_grad_gather_kernel<C, 2><<<ggrid, 256, 0, st>>>((const float*)ws, b, h, w, scale, g1, g2);
+            } else {
+                uvem_ce_grad_block_kernel<C, 1><<<(unsigned)((nblk + 3) / 4), 128, 0, st>>>(x1, x2, b, h, w, H, W, sy, sx, target, coef, (float*)ws);
+                uvem_ce_grad_gather_kernel<C, 1><<<ggrid, 256, 0, st>>>((const float*)ws, b, h, w, scale, g1, g2);
+            }
+        });
+        UEM_CHECK_LAUNCH_N(2);
+        return 0;
+    }
     dim3 grid(w, h, b);
     UEM_DISPATCH_C(c, {
         if (x2) uvem_ce_grad_kernel<C, 2><<<grid, 32, 0, st>>>(x1, x2, h, w, H, W, sy, sx, target, coef, scale, g1, g2);
