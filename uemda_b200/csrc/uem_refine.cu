@@ -388,9 +388,18 @@ __device__ __forceinline__ float4 ldg_f4_l1(const float4* p) {
 #ifndef UEM_REFINE_COL_MINB_VX2
 #define UEM_REFINE_COL_MINB_VX2 3
 #endif
+#ifdef UEM_REFINE_TIMING
+// development (tools/refine_timing.py): per-CTA %globaltimer stamps {entry, ignored id loaded, first setup done, first row
+// landed, first row done, last row done, statistics flushed}
+__device__ unsigned long long g_refine_t[1024][8];
+#define UEM_T(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_refine_t[blockIdx.x][i] = t_; } } while (0)
+#else
+#define UEM_T(i) do { } while (0)
+#endif
 template <int C, int NT, int NS, int VX>
 __global__ void __launch_bounds__(NT, ((VX == 2 ? UEM_REFINE_COL_MINB_VX2 : UEM_REFINE_COL_MINB) * 128) / NT)
 refine_col_kernel(const RefineParams p, const int ncols_max) {
+    UEM_T(0);
     constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32, WC = 32 * VX;
     constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
     constexpr uint32_t kPlane = (uint32_t)WC * 4u;               // bytes of one soft plane of a warp row
@@ -467,6 +476,10 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
     const int64_t ignored_id = *p.ignored_id;
     const uint32_t ign_lo = ((uint64_t)ignored_id >> 32) == 0 ? (uint32_t)ignored_id : 0xffffffffu;
     const uint32_t Ru = (uint32_t)p.R;
+#ifdef UEM_REFINE_TIMING
+    if (ign_lo == 0x12345678u) return;   // force the load to complete before the stamp
+#endif
+    UEM_T(1);
 
     // column state: pre-scaled row-pair interpolants of the three maps (pairs of classes; padded slot -> e = 0)
     float2 A[VX][3][PC], D[VX][3][PC];
@@ -590,8 +603,10 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
                 }
             }
         }
+        if (it == 0) UEM_T(2);
         cp_async_wait_group<NS - 1>();   // this lane's chunks of row `it` have landed ...
         __syncwarp();                    // ... and so have the other lanes' (the row is read across lanes)
+        if (it == 0) UEM_T(3);
         if (active) {
             const uint32_t rd = rd_base + (uint32_t)stage * kWarpStage;   // this lane's first float of plane 0
             int64_t rid[VX];
@@ -691,11 +706,14 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
                 else *dst = o[ci][0];
             }
         }
+        if (it == 0) UEM_T(4);
         if (++y == H) { y = 0; ++bs; }
         pstage = stage;
         if (++stage == NS) stage = 0;
     }
+    UEM_T(5);
     if (p.stats) flush(cur_b);
+    UEM_T(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1388,6 +1406,14 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
 }
 
 }  // namespace
+
+#ifdef UEM_REFINE_TIMING
+extern "C" __attribute__((visibility("default"))) int uem_debug_refine_timing(unsigned long long* host_out /* [1024][8] */) {
+    UEM_CUDA(cudaDeviceSynchronize());
+    UEM_CUDA(cudaMemcpyFromSymbol(host_out, g_refine_t, sizeof(unsigned long long) * 1024 * 8));
+    return 0;
+}
+#endif
 
 extern "C" int uem_set_option(const char* name, int value) {
     UEM_REQUIRE(name, "uem_set_option: NULL name");
