@@ -696,19 +696,25 @@ def main():
     if pipe is not None:   # restore the pipeline invariant (phase A of the next set in place) for what follows
         barrier()
 
-    # ---- kernel-level timing: CUDA events recorded inside the C call around the fused refine kernel (eager steps)
+    # ---- kernel-level timing: CUDA events recorded inside the C call around the fused refine kernel, on the un-pipelined
+    # chain (region max -> Pearson -> refine -> selection back to back, the order of the public API call), inputs rotating
+    # over the buffer sets; a CUDA graph replay cannot carry per-kernel events, hence this separate eager loop
     refine_ms = None
     if pipe is not None:
         n_k = min(args.steps, 50)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
+        ws_k = torch.zeros(lib.uem_mine_ws_bytes(wl.b, wl.c, wl.H, wl.W, wl.h, wl.w, wl.k, capacity), dtype=torch.uint8, device=dev)
         with torch.cuda.stream(pipe.main):
             for a, b2 in evs:   # torch creates the cudaEvent_t lazily on the first record()
                 a.record()
                 b2.record()
             torch.cuda.synchronize()
             for i in range(n_k):
+                s_ = sets[i % len(sets)]
                 lib.uem_profile_refine_events(evs[i][0].cuda_event, evs[i][1].cuda_event)
-                pipe.run(1, serial=True)   # phases one after the other: the timed kernel has the GPU to itself
+                mining.refine_select(7, s_["soft"], TEMP, feat=s_["feat"], prototypes=pipe.proto_state, pred1=s_["pred1"],
+                                     pred2=s_["pred2"], sup=s_["sup"], num_regions=capacity, eps=pipe.al.eps,
+                                     select=(CUTOFF[0], CUTOFF[1], -1), ws=ws_k, uvem=UVEM)
         barrier()
         kern = []
         for a, b2 in evs:

@@ -1,7 +1,6 @@
-python -m pytest tests -m gpu -x -q -k "refine or golden or chain or oracle_mining or full_size or workspace" 2>&1 | tail -4
-K="--only label_refine,mine_chain --iters 120"
-echo "== form1 + prologue overlap + tap prefetch cfg2" > gpurun_out/r2_kb_refine6.txt; python tools/kbench.py $K --refine-form 1 >> gpurun_out/r2_kb_refine6.txt 2>&1
-echo "== cfg5" >> gpurun_out/r2_kb_refine6.txt; python tools/kbench.py $K --refine-form 1 --workload cfg5_sweep_32x6x512 >> gpurun_out/r2_kb_refine6.txt 2>&1
-echo "== cfg3" >> gpurun_out/r2_kb_refine6.txt; python tools/kbench.py $K --refine-form 1 --workload cfg3_loveda_16x7x1024 >> gpurun_out/r2_kb_refine6.txt 2>&1
-grep -v "^entry" gpurun_out/r2_kb_refine6.txt
-python tools/refine_timing.py > gpurun_out/r2_refine_timeline_b.txt 2>&1; cat gpurun_out/r2_refine_timeline_b.txt
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_final_a.json 2> gpurun_out/r2_bench_final_a.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_a.csv python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/ncu_launch_a.log 2>&1
+tail -c 600 gpurun_out/r2_bench_final_a.err; tail -2 gpurun_out/ncu_launch_a.log | cut -c1-300
+python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline --no-e2e > gpurun_out/plain_b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:refine_col_kernel -s 30 -c 2 -o gpurun_out/prof_refine_r02 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_b.log 2>&1
+tail -2 gpurun_out/ncu_full_b.log | cut -c1-300
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_ref_final_a.json 2> gpurun_out/r2_ref_final_a.err
