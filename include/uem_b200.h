@@ -240,6 +240,9 @@ UEM_API int uem_class_hist_i64(const int64_t* label, int64_t n, int c, int64_t i
 UEM_API int uem_class_weight_lookup_f32(const int64_t* label, int64_t n, int c, int64_t ignore_label,
                                 const float* table, float* out, void* stream);
 UEM_API int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float hi, int64_t* hist, void* stream);
+/* torch.bucketize(x, boundaries) (right=False; balance.py:194,263): inds[i] = number of boundaries < x[i]; boundaries
+ * (device, ascending, nb <= 1024).  NaN -> nb, like torch. */
+UEM_API int uem_bucketize_f32(const float* x, int64_t n, const float* boundaries, int nb, int64_t* inds, void* stream);
 
 /* ---- offline pseudo-label regeneration (next row) ------------------------------
  * pseudo_generation.py:150-151, vis_corrected_pseudo_labels.py:191: the map written to disk is

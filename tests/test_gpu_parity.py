@@ -1160,3 +1160,14 @@ def test_uvem_loss_backward_forms_agree(dev, shape, heads):
         assert torch.equal(a[m], a2[m]), "backward is not bit-reproducible"
         tol = 1e-5 * float(r[m].abs().max())
         assert_close(a[m], r[m], rtol=1e-4, atol=tol, what="backward forms, head %d" % m)
+
+
+def test_bucketize_matches_torch(dev):
+    """a15 companion: torch.bucketize over the 31 edges of the GHM / GDP gradient-norm bins (balance.py:194,263),
+    including values on the edges, outside [0, 1], the -1 marker of ignored pixels, NaN and infinities."""
+    from uemda_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    edges = torch.arange(31).float() / 30
+    x = torch.cat([torch.rand(100000, generator=g) * 1.4 - 0.2, edges, torch.tensor([-1.0, float("nan"), float("inf"), -float("inf")])])
+    _eq(ops.bucketize(x.to(dev), edges.to(dev)), torch.bucketize(x, edges), "bucketize")
+    _eq(ops.bucketize(x.reshape(-1, 5)[:100].to(dev), edges.to(dev)), torch.bucketize(x.reshape(-1, 5)[:100], edges), "bucketize 2-d")

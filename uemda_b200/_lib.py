@@ -67,6 +67,7 @@ SIGNATURES = {
     "uem_class_hist_i64": (_I, [_P, _L, _I, _L, _P, _P]),
     "uem_class_weight_lookup_f32": (_I, [_P, _L, _I, _L, _P, _P, _P]),
     "uem_hist_f32": (_I, [_P, _L, _I, _F, _F, _P, _P]),
+    "uem_bucketize_f32": (_I, [_P, _L, _P, _I, _P, _P]),
     "uem_label_plus1_u8_i64": (_I, [_P, _L, _P, _P]),
     "uem_pcl_ws_bytes": (_L, [_I, _I, _L]),
     "uem_pcl_forward_f32": (_I, [_P, _I, _I, _L, _P, _I, _P, _L, _F, _P, _P, _P, _P]),

@@ -144,6 +144,36 @@ extern "C" int uem_hist_f32(const float* x, int64_t n, int bins, float lo, float
     return 0;
 }
 
+// torch.bucketize(x, boundaries) (right=False), balance.py:194,263: inds[i] = number of boundaries < x[i]
+// (NaN and +inf -> nb, -inf -> 0); boundaries sorted ascending, nb <= 1024 (kept in shared memory, binary search)
+namespace {
+__global__ void __launch_bounds__(256) bucketize_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ bounds, int nb,
+                                                        int64_t* __restrict__ inds) {
+    extern __shared__ float sb[];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sb[i] = bounds[i];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        int lo = 0, hi = nb;                     // first index with bounds[idx] >= v (lower_bound); NaN: every test is false -> nb
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (!(sb[mid] >= v)) lo = mid + 1;
+            else hi = mid;
+        }
+        inds[i] = lo;
+    }
+}
+}  // namespace
+
+extern "C" int uem_bucketize_f32(const float* x, int64_t n, const float* boundaries, int nb, int64_t* inds, void* stream) {
+    UEM_REQUIRE(x && boundaries && inds && n >= 0 && nb > 0 && nb <= 1024, "uem_bucketize_f32: bad arguments (1..1024 boundaries)");
+    if (n == 0) return 0;
+    const int grid = (int)min((int64_t)UEM_SMS * 8, (n + 255) / 256);
+    bucketize_kernel<<<grid, 256, nb * sizeof(float), (cudaStream_t)stream>>>(x, n, boundaries, nb, inds);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int uem_label_plus1_u8_i64(const int64_t* label, int64_t n, uint8_t* out, void* stream) {
     UEM_REQUIRE(label && out && n > 0, "uem_label_plus1_u8_i64: bad arguments");
     const int vec = uem_aligned16(label) && ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);

@@ -421,6 +421,18 @@ def hist_f32(x, bins, lo, hi):
     return hist
 
 
+def bucketize(x, boundaries):
+    """torch.bucketize(x, boundaries) (right=False) as int64 (balance.py:194,263: gradient-norm bins of GHM / GDP)."""
+    L.require_cuda(x, boundaries)
+    shape = x.shape
+    x = L.f32c(x.detach()).reshape(-1)
+    boundaries = L.f32c(boundaries.detach()).reshape(-1)
+    lib = L.bind(x)
+    out = torch.empty(x.numel(), dtype=torch.int64, device=x.device)
+    L.check(lib.uem_bucketize_f32(L.ptr(x), x.numel(), L.ptr(boundaries), boundaries.numel(), L.ptr(out), L.stream_of(x)))
+    return out.reshape(shape)
+
+
 # --------------------------------------------------------------------------------------------- regeneration
 def label_plus1_u8(label):
     """uint8(label + 1): the on-disk form of a hard pseudo-label map (pseudo_generation.py:150-151)."""
