@@ -340,11 +340,16 @@ class Pipeline:
         s = self.sets[j]
         self.local_ids[j] = self.mining.region_phase(s["soft"], s["sup"], TEMP, self.R, self.ws[j], self.wl.h, self.wl.w, self.wl.k)
 
-    def send_part(self, j):
-        """N > 1: this rank's statistics of step j into every rank's slot; the same launch polls the other ranks' max ids
-        and leaves the batch-global ignored id (alignment.py:241) in a static tensor, one step ahead of its consumer."""
+    def send_id_part(self, j):
+        """N > 1: this rank's max id of step j into every rank's slot, right behind the region pass (one step ahead of its
+        consumer); the same launch polls the other ranks' ids and leaves the batch-global ignored id (alignment.py:241)."""
         if self.peer is not None:
-            self.miner.send_stats(self.partials[j], self.local_ids[j], j % self.peer.depth, global_id_out=self.ignored[j])
+            self.miner.send_stats(None, self.local_ids[j], j % self.peer.depth, global_id_out=self.ignored[j], part="id")
+
+    def send_sums_part(self, j):
+        """N > 1: prototype sums / counts of step j, at the head of step j's own Pearson branch: not at the tail of a graph"""
+        if self.peer is not None:
+            self.miner.send_stats(self.partials[j], None, j % self.peer.depth, part="sums")
 
     def ema_part(self, j):
         """prototype EMA of step j (alignment.py:347-353): its last reader (the Pearson pass of step j) ran one step earlier"""
@@ -380,11 +385,12 @@ class Pipeline:
         jn = (j + 1) % self.n
         if serial:
             self.refine_part(j)
+            self.send_sums_part(j)
             self.ema_part(j)
             self.proto_part(jn)
             self.region_part(jn)
+            self.send_id_part(jn)
             self.source_part(jn)
-            self.send_part(jn)
             return
         for st in (self.br_region, self.br_source, self.br_proto):
             st.wait_stream(cur)
@@ -392,19 +398,20 @@ class Pipeline:
             self.source_part(jn)
         with torch.cuda.stream(self.br_region):
             self.region_part(jn)
-            self.br_region.wait_stream(self.br_source)
-            self.send_part(jn)
+            self.send_id_part(jn)
         with torch.cuda.stream(self.br_proto):
+            self.send_sums_part(j)
             self.ema_part(j)
             self.proto_part(jn)
         self.refine_part(j)
         cur.wait_stream(self.br_proto)
         cur.wait_stream(self.br_region)
+        cur.wait_stream(self.br_source)
 
     def timeline(self, steps=12):
         """development aid: the parts of a step run one after the other on the main stream with a CUDA event between them;
         returns {part: mean microseconds} (no overlap, every part pays its own launch ramp and tail)."""
-        names = ["refine+select", "ema", "proto", "region", "source", "send"]
+        names = ["refine+select", "send sums+ema", "proto", "region", "send id", "source"]
         acc = {k: 0.0 for k in names}
         with torch.cuda.stream(self.main):
             for _ in range(steps):
@@ -414,15 +421,16 @@ class Pipeline:
                 ev[0].record()
                 self.refine_part(j)
                 ev[1].record()
+                self.send_sums_part(j)
                 self.ema_part(j)
                 ev[2].record()
                 self.proto_part(jn)
                 ev[3].record()
                 self.region_part(jn)
                 ev[4].record()
-                self.source_part(jn)
+                self.send_id_part(jn)
                 ev[5].record()
-                self.send_part(jn)
+                self.source_part(jn)
                 ev[6].record()
                 self.pos += 1
                 torch.cuda.synchronize()
@@ -437,7 +445,7 @@ class Pipeline:
             self.proto_part(0)
             self.region_part(0)
             self.source_part(0)
-            self.send_part(0)
+            self.send_id_part(0)
         self.main.synchronize()
         self.pos = 0
 

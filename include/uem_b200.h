@@ -310,6 +310,9 @@ UEM_API int uem_views_mean_f32(const float* views, int n, int64_t numel, float* 
  *   stores the vector into slot [slot][rank] of every peer; waits (bounded) for the peers' acknowledgement of the
  *   previous use of that slot first.  global_id_out (optional): the same launch then also polls the other ranks' max ids of
  *   this step and writes the batch-global max id there (what wait_maxid would return), saving that launch.
+ *   parts: bit 0 = sums + counts + histogram, bit 1 = max id, bit 2 = this is the step's last send into the slot (advances
+ *   the sequence number); 7 = everything in one launch.  A step may send the id early (parts = 2, partials_ws NULL: the id
+ *   is known after the region pass) and the sums later (parts = 5): every word carries the step's sequence number itself.
  * wait_maxid: blocks the stream (bounded spin in a one-warp kernel) until every rank's vector of this slot has arrived;
  *   writes the batch-global max id.  fold_finalize_ema: (after wait_maxid on the same stream) folds the ranks in rank
  *   order -> keep-old rule -> EMA (alignment.py:347-353,463-466; proto_new may alias proto_old; NULL = no EMA), optional
@@ -321,7 +324,7 @@ UEM_API int uem_views_mean_f32(const float* views, int n, int64_t numel, float* 
 UEM_API int64_t uem_xchg_region_bytes(int world, int depth, int c, int k);
 UEM_API int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
                       const void* const* peer_regions, int rank, int world, int depth, int slot, int64_t* global_id_out,
-                      void* stream);
+                      int parts, void* stream);
 UEM_API int uem_xchg_wait_maxid(void* region, int world, int depth, int slot, int c, int k, int64_t* max_id_out, void* stream);
 UEM_API int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, int rank, int world, int depth, int slot, int c,
                                    int k, const float* proto_old, float eps, float one_minus_decay, float decay,

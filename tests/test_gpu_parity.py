@@ -993,8 +993,14 @@ def test_peer_exchange_emulated_ranks(dev, world, depth):
         hists = [ops.class_hist(labs[r], c) for r in range(world)]
         parts = [ops.proto_accumulate(feats[r], labs[r], c, -1, fold=False) for r in range(world)]
         gid = torch.zeros(1, dtype=torch.int64, device=dev)
-        for r in range(world):   # the last sender finds every other rank's id already there: it may poll for the global id
-            xs[r].send(parts[r], ids[r], slot, hist=hists[r], global_id_out=gid if r == world - 1 else None)
+        if step % 2 == 0:   # one launch per rank; the last sender finds every other id already there and may poll for the global id
+            for r in range(world):
+                xs[r].send(parts[r], ids[r], slot, hist=hists[r], global_id_out=gid if r == world - 1 else None)
+        else:               # the split form: ids early (right after the region pass), sums later; same sequence number
+            for r in range(world):
+                xs[r].send(None, ids[r], slot, global_id_out=gid if r == world - 1 else None, part="id")
+            for r in range(world):
+                xs[r].send(parts[r], None, slot, hist=hists[r], part="sums")
         assert int(gid) == max(int(i) for i in ids), "global id from the fused send"
         got_ids, got_hist = [], []
         for r in range(world):

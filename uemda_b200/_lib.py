@@ -83,7 +83,7 @@ SIGNATURES = {
     "uem_window_average_f32": (_I, [_P, _P, _I, _I, _L, _P]),
     "uem_views_mean_f32": (_I, [_P, _I, _L, _P, _P]),
     "uem_xchg_region_bytes": (_L, [_I, _I, _I, _I]),
-    "uem_xchg_send_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "uem_xchg_send_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "uem_xchg_wait_maxid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "uem_xchg_fold_finalize_ema_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
     "uem_xchg_status": (_I, [_P, _P, _P]),

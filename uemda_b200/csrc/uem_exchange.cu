@@ -113,7 +113,7 @@ __device__ __forceinline__ int64_t ll_load_i64(const char* src, unsigned seq, bo
 __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial, int b,
                                                         int c, int k, const int64_t* __restrict__ max_id,
                                                         const int64_t* __restrict__ hist, const Peers peers, int rank, int world,
-                                                        int slot, int64_t* __restrict__ global_id_out) {
+                                                        int slot, int64_t* __restrict__ global_id_out, int parts) {
     const int ch = blockIdx.x, p = blockIdx.y;
     char* const mine = peers.base[rank];
     XHeader* hdr = reinterpret_cast<XHeader*>(mine);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
     char* dst = peers.base[p] + kOffSlots + ((int64_t)slot * world + rank) * sb;
     // chunk ch of the sums, 4 floats at a time; per-image partials folded in image order (the same fp32 additions as
     // proto_fold_kernel / proto_fold_finalize_kernel: a one-rank exchange reproduces the single-GPU step bit for bit)
-    const int nvec = (ck + 3) / 4;
+    const int nvec = (parts & 1) ? (ck + 3) / 4 : 0;   // parts bit 0: sums + counts + histogram; bit 1: max id
     const int v0 = (int)((int64_t)nvec * ch / gridDim.x), v1 = (int)((int64_t)nvec * (ch + 1) / gridDim.x);
     for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
         float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
 #pragma unroll
         for (int u = 0; u < 4; ++u) ll_store(dst + ((int64_t)4 * v + u) * 8, __float_as_uint(s[u]), my);
     }
-    if (ch == 0 && threadIdx.x < 2 * c + 2) {
+    if (ch == 0 && threadIdx.x < 2 * c + 2 && ((threadIdx.x == 2 * c + 1) ? (parts & 2) : (parts & 1))) {
         char* tail = dst + sum_words(c, k) * 8;
         const int i = threadIdx.x;
         int64_t v;
@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
         }
         if (r == 0) global_id_out[0] = id;
     }
-    // the last CTA of the launch advances the local sequence number (every CTA has read it by then)
+    // the last CTA of the FINAL launch of a step (parts bit 2) advances the local sequence number (every CTA has read it by
+    // then); an earlier partial launch of the same step leaves it alone, so both tag their words with the same number
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && (parts & 4)) {
         __threadfence();
         const unsigned old = atomicAdd(&hdr->arrive_all[slot], 1u);
         if (old == gridDim.x * gridDim.y - 1) {
@@ -290,14 +291,15 @@ extern "C" int64_t uem_xchg_region_bytes(int world, int depth, int c, int k) {
 
 extern "C" int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, const int64_t* max_id, const int64_t* hist,
                                  const void* const* peer_regions, int rank, int world, int depth, int slot, int64_t* global_id_out,
-                                 void* stream) {
-    UEM_REQUIRE(partials_ws && b > 0 && c > 0 && c <= UEM_MAX_C && k > 0, "uem_xchg_send_f32: bad arguments");
+                                 int parts, void* stream) {
+    UEM_REQUIRE(b > 0 && c > 0 && c <= UEM_MAX_C && k > 0 && (parts & 3) && !(parts & ~7), "uem_xchg_send_f32: bad arguments");
+    UEM_REQUIRE(!(parts & 1) || partials_ws, "uem_xchg_send_f32: the sums part needs the partials");
     Peers P;
     if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_send_f32")) return rc;
     const float* partial = (const float*)partials_ws;
-    const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
-    xchg_send_kernel<<<dim3(kSendChunks, world), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, max_id, hist, P, rank, world,
-                                                                                slot, global_id_out);
+    const int* cnt_partial = partial ? (const int*)(partial + (int64_t)b * c * k) : nullptr;
+    xchg_send_kernel<<<dim3((parts & 1) ? kSendChunks : 1, world), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, max_id, hist,
+                                                                                                  P, rank, world, slot, global_id_out, parts);
     UEM_CHECK_LAUNCH();
     return 0;
 }

@@ -123,17 +123,22 @@ class PeerExchange:
         return [cls(ptrs, r, world, c, k, depth, device, keep=regions, backend="local") for r in range(world)]
 
     # ------------------------------------------------------------------ the three launches (capturable)
-    def send(self, partials, max_id, slot, hist=None, global_id_out=None):
+    def send(self, partials, max_id, slot, hist=None, global_id_out=None, part="all"):
         """partials: ``ops.proto_accumulate(..., fold=False)`` of this rank's source shard; max_id: (1,) int64 rank-local
         max superpixel id (or None); hist: (c+1,) int64 class histogram of this rank's labels (or None).
         global_id_out: optional (1,) int64 tensor; the launch then also polls the other ranks' ids of this step and leaves the
-        batch-global max id there (= ``wait_max_id`` without its own launch)."""
-        ws, (b, c, k) = partials
-        assert (c, k) == (self.c, self.k)
+        batch-global max id there (= ``wait_max_id`` without its own launch).
+        part: "all" | "id" (only the max id; ``partials`` may be None) | "sums" (everything else; ends the step's send)."""
+        parts = {"all": 7, "id": 2, "sums": 5}[part]   # "id" early + "sums" later = one step sent in two launches
+        ws, b = None, 1
+        if parts & 1:
+            ws, (b, c, k) = partials
+            assert (c, k) == (self.c, self.k)
+        anchor = ws if ws is not None else max_id
         L.require_cuda(ws, max_id, hist, global_id_out)
-        lib = L.bind(ws)
-        L.check(lib.uem_xchg_send_f32(L.ptr(ws), b, c, k, L.ptr(max_id), L.ptr(hist), self._arr, self.rank, self.world, self.depth,
-                                      int(slot), L.ptr(global_id_out), L.stream_of(ws)))
+        lib = L.bind(anchor)
+        L.check(lib.uem_xchg_send_f32(L.ptr(ws), b, self.c, self.k, L.ptr(max_id), L.ptr(hist), self._arr, self.rank, self.world,
+                                      self.depth, int(slot), L.ptr(global_id_out), parts, L.stream_of(anchor)))
 
     def wait_max_id(self, slot, out=None):
         """Blocks the current stream until every rank's vector of ``slot`` has arrived -> batch-global max id (1,) int64."""

@@ -263,12 +263,13 @@ class ShardedMiner:
                     raise
 
     # ---- device-side form (one or two CUDA graphs per step, no host-issued collective): send -> receive_id -> apply_peer
-    def send_stats(self, partials, local_max_id, slot, hist=None, global_id_out=None):
+    def send_stats(self, partials, local_max_id, slot, hist=None, global_id_out=None, part="all"):
         """Capturable.  partials: ops.proto_accumulate(feat_s, down, ..., fold=False); local_max_id: what region_phase
         returned; hist: optional (c+1,) class histogram of this rank's labels.  Stores this rank's vector into slot
         ``slot`` of every rank; with ``global_id_out`` the same launch waits for the other ranks' ids and leaves the
-        batch-global ignored id there (then ``receive_id`` is not needed)."""
-        self.peer.send(partials, local_max_id, slot, hist=hist, global_id_out=global_id_out)
+        batch-global ignored id there (then ``receive_id`` is not needed).  part="id" right after the region pass and
+        part="sums" once the source statistics exist split the send so that neither sits at the tail of a step."""
+        self.peer.send(partials, local_max_id, slot, hist=hist, global_id_out=global_id_out, part=part)
 
     def receive_id(self, slot, out=None):
         """Capturable.  Blocks the stream until every rank's vector has arrived -> batch-global ignored id (alignment.py:241)."""
