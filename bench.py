@@ -297,6 +297,10 @@ class Pipeline:
         self.wl, self.sets, self.R, self.dev, self.miner = wl, sets, capacity, dev, miner
         self.mining, self.ops = mining, ops
         self.lib = _lib.load()
+        # pipelined schedule: the region-max kernel at ONE 512-thread CTA per SM leaves half the register file to the kernels
+        # of the other branches (two-stream step at config 2: 86.5 vs 91.0 us); the un-pipelined public path keeps two
+        if not any(o.startswith("region_ctas_per_sm=") for o in getattr(Pipeline, "cli_opts", [])):
+            self.lib.uem_set_option(b"region_ctas_per_sm", 1)
         self.n = len(sets)
         if miner is not None:
             self.al = miner.aligner
@@ -326,6 +330,14 @@ class Pipeline:
         self.br_source = torch.cuda.Stream(device=dev, priority=pr[3])
         self.use_graph = use_graph
         self.graphs = None
+        # two_stream: refine -> selection (M) and the rest of a step (A) as two graphs on two streams tied by events, so a
+        # step's tail overlaps the next step's head instead of one drain per step: M(i) waits for A(i-1), A(i) for M(i-2)
+        self.two_stream = os.environ.get("UEM_BENCH_TWO_STREAM", "1") == "1"
+        self.split_fold = os.environ.get("UEM_BENCH_SPLIT_FOLD", "0") == "1"
+        self.ahead_stream = self.br_proto
+        self.ev_m = [torch.cuda.Event() for _ in range(self.n)]
+        self.ev_a = [torch.cuda.Event() for _ in range(self.n)]
+        self.graphs_a = None
         self.peer = miner.peer if miner is not None else None
 
     # ---- the parts of a step
@@ -347,14 +359,17 @@ class Pipeline:
             self.miner.send_stats(None, self.local_ids[j], j % self.peer.depth, global_id_out=self.ignored[j], part="id")
 
     def send_sums_part(self, j):
-        """N > 1: prototype sums / counts of step j, at the head of step j's own Pearson branch: not at the tail of a graph"""
-        if self.peer is not None:
+        """N > 1: prototype sums / counts of step j, at the head of step j's own Pearson branch: not at the tail of a graph.
+        Merged into the fold + EMA launch (ema_part) unless UEM_BENCH_SPLIT_FOLD=1."""
+        if self.peer is not None and self.split_fold:
             self.miner.send_stats(self.partials[j], None, j % self.peer.depth, part="sums")
 
     def ema_part(self, j):
         """prototype EMA of step j (alignment.py:347-353): its last reader (the Pearson pass of step j) ran one step earlier"""
-        if self.peer is not None:
+        if self.peer is not None and self.split_fold:
             self.miner.apply_peer(j % self.peer.depth, in_place=True)
+        elif self.peer is not None:
+            self.miner.exchange_apply(self.partials[j], j % self.peer.depth, in_place=True)   # send + poll + fold + EMA
         else:
             self.ops.proto_fold_finalize(self.partials[j], self.proto_state, eps=self.al.eps, decay=DECAY, out=self.proto_state)
 
@@ -392,6 +407,10 @@ class Pipeline:
             self.send_id_part(jn)
             self.source_part(jn)
             return
+        if self.two_stream:
+            self.ahead_body(j)
+            self.refine_part(j)
+            return
         for st in (self.br_region, self.br_source, self.br_proto):
             st.wait_stream(cur)
         with torch.cuda.stream(self.br_source):
@@ -405,6 +424,23 @@ class Pipeline:
             self.proto_part(jn)
         self.refine_part(j)
         cur.wait_stream(self.br_proto)
+        cur.wait_stream(self.br_region)
+        cur.wait_stream(self.br_source)
+
+    def ahead_body(self, j):
+        """everything of step j except refine -> selection, as three branches forked from / joined to the current stream"""
+        cur = torch.cuda.current_stream(self.dev)
+        jn = (j + 1) % self.n
+        self.br_region.wait_stream(cur)
+        self.br_source.wait_stream(cur)
+        with torch.cuda.stream(self.br_source):
+            self.source_part(jn)
+        with torch.cuda.stream(self.br_region):
+            self.region_part(jn)
+            self.send_id_part(jn)
+        self.send_sums_part(j)
+        self.ema_part(j)
+        self.proto_part(jn)
         cur.wait_stream(self.br_region)
         cur.wait_stream(self.br_source)
 
@@ -454,13 +490,21 @@ class Pipeline:
             return False
         try:
             # capturing records the launches without running them: the exchange sequence numbers do not move
-            graphs = []
+            graphs, graphs_a = [], []
             for j in range(self.n):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.main):
-                    self.step_body(j)
+                if self.two_stream:
+                    ga = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(ga, stream=self.ahead_stream):
+                        self.ahead_body(j)
+                    graphs_a.append(ga)
+                    with torch.cuda.graph(g, stream=self.main):
+                        self.refine_part(j)
+                else:
+                    with torch.cuda.graph(g, stream=self.main):
+                        self.step_body(j)
                 graphs.append(g)
-            self.graphs = graphs
+            self.graphs, self.graphs_a = graphs, graphs_a
             return True
         except Exception as e:  # noqa: BLE001
             print("graph capture failed, timing eagerly: %r" % (e,), file=sys.stderr)
@@ -471,6 +515,24 @@ class Pipeline:
     def run(self, cnt, eager=False, serial=False):
         """the next `cnt` steps of the sequence on the main stream; returns the set index of the last one"""
         j = None
+        if self.two_stream and self.graphs is not None and not eager and not serial:
+            sa, sm = self.ahead_stream, self.main
+            sa.wait_stream(sm)            # whatever ran before (eager steps on the main stream) is ordered before this burst
+            for e in self.ev_m + self.ev_a:
+                e.record(sm)
+            for _ in range(cnt):
+                j = self.pos % self.n
+                with torch.cuda.stream(sa):
+                    sa.wait_event(self.ev_m[(j + 1) % self.n])     # M(i-2): last reader of the buffers A(i) refills (n = 3)
+                    self.graphs_a[j].replay()
+                    self.ev_a[j].record(sa)
+                with torch.cuda.stream(sm):
+                    sm.wait_event(self.ev_a[(j - 1) % self.n])     # A(i-1) prepared set j
+                    self.graphs[j].replay()
+                    self.ev_m[j].record(sm)
+                self.pos += 1
+            sm.wait_stream(sa)            # the burst ends when both streams are done
+            return j
         with torch.cuda.stream(self.main):
             for _ in range(cnt):
                 j = self.pos % self.n
@@ -662,6 +724,7 @@ def main():
     for kv in args.opt:
         name, val = kv.split("=")
         _lib.check(lib.uem_set_option(name.encode(), int(val)))
+    Pipeline.cli_opts = list(args.opt)
     config.strict_asserts = False
 
     inp, sets, capacity = make_sets(wl, args.sets, dev, rank, world)
@@ -743,6 +806,7 @@ def main():
     if world > 1 and not args.no_parity:
         parity = sharded_parity(wl, inp, sets, capacity, miner, pipe, dev, rank, world, args)
 
+    lib.uem_set_option(b"region_ctas_per_sm", 0)   # the public, un-pipelined path below runs the library defaults
     # ---- e2e: public drop-in API, host (pinned) inputs, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:

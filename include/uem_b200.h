@@ -329,6 +329,14 @@ UEM_API int uem_xchg_wait_maxid(void* region, int world, int depth, int slot, in
 UEM_API int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, int rank, int world, int depth, int slot, int c,
                                    int k, const float* proto_old, float eps, float one_minus_decay, float decay,
                                    float* proto_new, float* sums_out, int64_t* counts_out, int64_t* hist_out, void* stream);
+/* send (sums part) + fold_finalize_ema in ONE launch: every thread carries its element of the (c,k) bank from this rank's
+ * per-image partials through the LL stores into every rank's slot, the poll of every rank's words and the rank-ordered
+ * fold to the EMA-updated prototype (the max id of the step has been sent before with parts = 2).  Not for emulated ranks
+ * on one device: every rank's launch must be able to run while the others' are running. */
+UEM_API int uem_xchg_exchange_fold_ema_f32(const void* partials_ws, int b, int c, int k, const int64_t* hist,
+                                   const void* const* peer_regions, int rank, int world, int depth, int slot,
+                                   const float* proto_old, float eps, float one_minus_decay, float decay, float* proto_new,
+                                   float* sums_out, int64_t* counts_out, int64_t* hist_out, void* stream);
 UEM_API int uem_xchg_status(const void* region, int* status_out, void* stream);
 /* cudaIpc plumbing for the region when torch symmetric memory is unavailable: alloc (cudaMalloc + zero) returns the local
  * pointer and a 64-byte handle to ship to the peers (any host channel), open maps a peer's handle. */

@@ -1177,3 +1177,33 @@ def test_bucketize_matches_torch(dev):
     x = torch.cat([torch.rand(100000, generator=g) * 1.4 - 0.2, edges, torch.tensor([-1.0, float("nan"), float("inf"), -float("inf")])])
     _eq(ops.bucketize(x.to(dev), edges.to(dev)), torch.bucketize(x, edges), "bucketize")
     _eq(ops.bucketize(x.reshape(-1, 5)[:100].to(dev), edges.to(dev)), torch.bucketize(x.reshape(-1, 5)[:100], edges), "bucketize 2-d")
+
+
+def test_peer_exchange_merged_launch_world_of_one(dev):
+    """The merged send + poll + fold + EMA launch (uem_xchg_exchange_fold_ema_f32) in a world of one rank (on real ranks
+    every launch must run while the others run, so more ranks cannot be emulated in sequence on one device; bench.py
+    --gpus N checks them against a one-GPU run): bit-equal to the plain image-order fold + EMA, over slot reuse."""
+    from uemda_b200 import ops
+    from uemda_b200.exchange import PeerExchange
+    c, k, h, w, b = 6, 256, 8, 8, 3
+    g = torch.Generator().manual_seed(4)
+    x = PeerExchange.local_only(1, c, k, depth=3, device=dev)[0]
+    bank = torch.randn(c, k, generator=g).to(dev)
+    ref = bank.clone()
+    gid = torch.zeros(1, dtype=torch.int64, device=dev)
+    for step in range(7):
+        slot = step % 3
+        feat = torch.randn(b, k, h, w, generator=g).to(dev)
+        lab = torch.randint(-1, c if step != 2 else 3, (b, 1, h, w), generator=g).to(dev)
+        mid = torch.randint(0, 1 << 33, (1,), generator=g).to(dev)
+        hist = ops.class_hist(lab, c)
+        part = ops.proto_accumulate(feat, lab, c, -1, fold=False)
+        x.send(None, mid, slot, global_id_out=gid, part="id")
+        _, sums, counts, hout = x.exchange_fold(part, slot, bank, decay=0.9, out=bank, hist=hist, want_sums=True, want_hist=True)
+        assert x.status() == 0 and int(gid) == int(mid)
+        s1, n1 = ops.proto_accumulate(feat, lab, c, -1)
+        assert torch.equal(sums, s1)
+        _eq(counts, n1, "counts")
+        _eq(hout, hist, "histogram")
+        _, ref = ops.proto_finalize(s1, n1, ref, decay=0.9, want_local=False)
+        assert torch.equal(bank, ref), "merged exchange launch differs from fold + EMA at step %d" % step

@@ -86,6 +86,7 @@ SIGNATURES = {
     "uem_xchg_send_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "uem_xchg_wait_maxid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "uem_xchg_fold_finalize_ema_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
+    "uem_xchg_exchange_fold_ema_f32": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P]),
     "uem_xchg_status": (_I, [_P, _P, _P]),
     "uem_peer_alloc": (_I, [_L, _P, _P]),
     "uem_peer_open": (_I, [_P, _P]),

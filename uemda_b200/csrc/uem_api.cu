@@ -5,6 +5,7 @@
 static thread_local char g_err[512] = "";
 int g_uem_refine_ctas_per_sm = 0;
 int g_uem_region_ctas_per_sm = 0;
+int g_uem_proto_ctas_per_sm = 0;
 
 int uem_fail(const char* fmt, ...) {
     va_list ap;

@@ -15,6 +15,7 @@ int uem_fail(const char* fmt, ...);
 // tuning knobs set through uem_set_option (0 = the kernel's own choice); see uem_api.cu
 extern int g_uem_refine_ctas_per_sm;   // cap on resident CTAs per SM of the fused refine kernel (co-residency with the next batch's streaming kernels)
 extern int g_uem_region_ctas_per_sm;   // same for the region-max kernel
+extern int g_uem_proto_ctas_per_sm;    // same for the prototype-sum kernel (so that a Pearson CTA fits beside it)
 void uem_note_launches(int n);  // bookkeeping for uem_kernel_launches()
 void uem_take_profile_events(void** start, void** stop);
 

@@ -272,6 +272,97 @@ __global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers pee
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One launch per step for the sums: local fold -> LL stores into every rank's slot -> poll every rank's words -> rank-ordered
+// fold -> keep-old rule -> EMA -> acknowledgement.  Thread i owns element i of the (c,k) bank from its own partials to the
+// new prototype; CTA 0 also carries the counts / histogram words.  (The max id travels earlier, uem_xchg_send_f32 with
+// parts = 2, tagged with the same sequence number.)  A CTA sends before it polls and its peers' CTAs do the same, so no
+// poll waits for anything that is queued behind this launch on any GPU.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xchg_exchange_fold_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial,
+                                                                 int b, int c, int k, const int64_t* __restrict__ hist, const Peers peers,
+                                                                 int rank, int world, int slot, const float* __restrict__ proto_old,
+                                                                 float eps, float one_minus_decay, float decay,
+                                                                 float* __restrict__ proto_new, float* __restrict__ sums_out,
+                                                                 int64_t* __restrict__ counts_out, int64_t* __restrict__ hist_out) {
+    char* const mine = peers.base[rank];
+    XHeader* hdr = reinterpret_cast<XHeader*>(mine);
+    __shared__ unsigned s_my;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_my = *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) + 1u;
+    __syncthreads();
+    const unsigned my = s_my;
+    if (threadIdx.x < world) {   // every peer must have folded the previous contents of this slot
+        const unsigned* ack = reinterpret_cast<const unsigned*>(mine + kOffAcks) + slot * kMaxWorld + threadIdx.x;
+        if (!spin_until(ack, my - 1u)) atomicOr(&hdr->status, 8);
+    }
+    __syncthreads();
+    const int ck = c * k;
+    const int64_t sb = slot_bytes(c, k);
+    const int64_t my_off = kOffSlots + ((int64_t)slot * world + rank) * sb;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    // ---- send: this rank's element i (per-image partials folded in image order) into every rank's slot
+    if (i < ck) {
+        float s = 0.f;
+        for (int bi = 0; bi < b; ++bi) s += __ldg(partial + (int64_t)bi * ck + i);
+        for (int p = 0; p < world; ++p) ll_store(peers.base[p] + my_off + (int64_t)i * 8, __float_as_uint(s), my);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 2 * c + 1) {
+        const int t = threadIdx.x;
+        int64_t v = 0;
+        if (t < c) { for (int bi = 0; bi < b; ++bi) v += cnt_partial[bi * c + t]; }
+        else v = hist ? hist[t - c] : 0;
+        for (int p = 0; p < world; ++p) {
+            char* tail = peers.base[p] + my_off + sum_words(c, k) * 8 + (int64_t)t * 16;
+            ll_store(tail, (unsigned)((uint64_t)v & 0xffffffffu), my);
+            ll_store(tail + 8, (unsigned)((uint64_t)v >> 32), my);
+        }
+    }
+    // ---- receive + fold in rank order + EMA
+    const char* slots = mine + kOffSlots + (int64_t)slot * world * sb;
+    const char* tails = slots + sum_words(c, k) * 8;
+    bool ok = true;
+    if (i < ck) {
+        const int ci = i / k;
+        float s = 0.f;
+        int64_t n = 0;
+        for (int r = 0; r < world; ++r) {
+            const float v = __uint_as_float(ll_load(slots + r * sb + (int64_t)i * 8, my, &ok));
+            s = r ? s + v : v;
+            n += ll_load_i64(tails + r * sb + (int64_t)ci * 16, my, &ok);
+        }
+        if (sums_out) sums_out[i] = s;
+        if (proto_new) {
+            const float old = proto_old[i];
+            float local = s / ((float)n + eps);                 // alignment.py:348
+            if (n < 1) local = old;                             // :350
+            proto_new[i] = __fadd_rn(__fmul_rn(one_minus_decay, local), __fmul_rn(decay, old));   // :465
+        }
+    }
+    if (i < 2 * c + 1 && (counts_out || hist_out)) {
+        int64_t n = 0;
+        for (int r = 0; r < world; ++r) n += ll_load_i64(tails + r * sb + (int64_t)i * 16, my, &ok);
+        if (i < c) { if (counts_out) counts_out[i] = n; }
+        else if (hist_out) hist_out[i - c] = n;
+    }
+    if (!ok) atomicOr(&hdr->status, 8);
+    // ---- the last CTA acknowledges the slot to every peer and advances both sequence numbers
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&hdr->fold_arrive[slot], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<unsigned*>(peers.base[threadIdx.x] + kOffAcks) + slot * kMaxWorld + rank, my);
+        if (threadIdx.x == 0) {
+            hdr->fold_arrive[slot] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) = my;
+            *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) = my;
+        }
+    }
+}
+
 int fill_peers(Peers* P, const void* const* peer_regions, int rank, int world, int depth, int slot, const char* who) {
     UEM_REQUIRE(peer_regions && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "%s: bad rank/world (%d/%d, at most %d ranks)",
                 who, rank, world, kMaxWorld);
@@ -320,6 +411,23 @@ extern "C" int uem_xchg_fold_finalize_ema_f32(const void* const* peer_regions, i
     if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_fold_finalize_ema_f32")) return rc;
     xchg_fold_finalize_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, (cudaStream_t)stream>>>(
         P, rank, world, slot, c, k, proto_old, eps, one_minus_decay, decay, proto_new, sums_out, counts_out, hist_out);
+    UEM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int uem_xchg_exchange_fold_ema_f32(const void* partials_ws, int b, int c, int k, const int64_t* hist,
+                                              const void* const* peer_regions, int rank, int world, int depth, int slot,
+                                              const float* proto_old, float eps, float one_minus_decay, float decay, float* proto_new,
+                                              float* sums_out, int64_t* counts_out, int64_t* hist_out, void* stream) {
+    UEM_REQUIRE(partials_ws && b > 0 && c > 0 && c <= UEM_MAX_C && k > 0 && (!proto_new || proto_old),
+                "uem_xchg_exchange_fold_ema_f32: bad arguments");
+    Peers P;
+    if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_exchange_fold_ema_f32")) return rc;
+    const float* partial = (const float*)partials_ws;
+    const int* cnt_partial = (const int*)(partial + (int64_t)b * c * k);
+    xchg_exchange_fold_kernel<<<uem_div_up((int64_t)c * k, 256), 256, 0, (cudaStream_t)stream>>>(
+        partial, cnt_partial, b, c, k, hist, P, rank, world, slot, proto_old, eps, one_minus_decay, decay, proto_new, sums_out, counts_out,
+        hist_out);
     UEM_CHECK_LAUNCH();
     return 0;
 }

@@ -643,6 +643,7 @@ extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t
             int per_sm = 0;
             UEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, proto_accum_tma_kernel<C, UEM_PROTO_RW>, kTmaThreads, P::SMEM));
             if (per_sm < 1) per_sm = 1;
+            if (g_uem_proto_ctas_per_sm > 0 && per_sm > g_uem_proto_ctas_per_sm) per_sm = g_uem_proto_ctas_per_sm;
             const int total = b * uem_div_up(k, P::ROWS);
             const int nblk = min(total, UEM_SMS * per_sm);
             proto_accum_tma_kernel<C, UEM_PROTO_RW><<<nblk, kTmaThreads, P::SMEM, st>>>(tmap, k, (int)hw, b, label, ignore_label, partial,

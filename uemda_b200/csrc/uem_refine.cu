@@ -1419,6 +1419,7 @@ extern "C" int uem_set_option(const char* name, int value) {
     UEM_REQUIRE(name, "uem_set_option: NULL name");
     if (strcmp(name, "refine_ctas_per_sm") == 0) { g_uem_refine_ctas_per_sm = value; return 0; }
     if (strcmp(name, "region_ctas_per_sm") == 0) { g_uem_region_ctas_per_sm = value; return 0; }
+    if (strcmp(name, "proto_ctas_per_sm") == 0) { g_uem_proto_ctas_per_sm = value; return 0; }
     if (strcmp(name, "refine_form") == 0) { g_refine_form = value < 0 ? -1 : (value ? 1 : 0); return 0; }   // -1: back to the default
     return uem_fail("uem_set_option: unknown option '%s'", name);
 }

@@ -171,6 +171,31 @@ class PeerExchange:
                                                    L.ptr(hist), stream))
         return new, sums, counts, hist
 
+    def exchange_fold(self, partials, slot, proto_old=None, eps=1e-7, decay=None, out=None, hist=None, want_sums=False,
+                      want_hist=False):
+        """``send(part="sums")`` + ``fold_finalize`` in one launch (the step's max id must have been sent with part="id").
+        Every rank's launch has to be able to run while the others' run: real ranks only, or a world of one."""
+        ws, (b, c, k) = partials
+        assert (c, k) == (self.c, self.k)
+        L.require_cuda(ws, hist, proto_old)
+        dev = self.device
+        new = sums = counts = hist_out = None
+        omd = d = 0.0
+        if decay is not None:
+            proto_old = L.f32c(proto_old.detach())
+            new = out if out is not None else torch.empty_like(proto_old)
+            omd, d = ops.f32(1.0 - decay), ops.f32(decay)
+        if want_sums:
+            sums = torch.empty((self.c, self.k), dtype=torch.float32, device=dev)
+            counts = torch.empty((self.c,), dtype=torch.int64, device=dev)
+        if want_hist:
+            hist_out = torch.empty((self.c + 1,), dtype=torch.int64, device=dev)
+        lib = L.bind(ws)
+        L.check(lib.uem_xchg_exchange_fold_ema_f32(L.ptr(ws), b, c, k, L.ptr(hist), self._arr, self.rank, self.world, self.depth,
+                                                   int(slot), L.ptr(proto_old), ops.f32(eps), omd, d, L.ptr(new), L.ptr(sums),
+                                                   L.ptr(counts), L.ptr(hist_out), L.stream_of(ws)))
+        return new, sums, counts, hist_out
+
     def status(self):
         """Synchronises the current stream; 0 = fine, bit 8 = a bounded poll timed out (2 s)."""
         out = ctypes.c_int(0)

@@ -285,6 +285,15 @@ class ShardedMiner:
         al.prototypes = new
         return hist
 
+    def exchange_apply(self, partials, slot, in_place=True, hist=None, want_hist=False):
+        """Capturable: ``send_stats(part="sums")`` + ``apply_peer`` in ONE launch (alignment.py:347-353 over the global batch);
+        the step's max id has been sent with ``send_stats(None, local_max_id, slot, part="id")``."""
+        al = self.aligner
+        new, _, _, h = self.peer.exchange_fold(partials, slot, al.prototypes, eps=al.eps, decay=al.decay,
+                                               out=al.prototypes if in_place else None, hist=hist, want_hist=want_hist)
+        al.prototypes = new
+        return h
+
     # ---- class histogram over the global batch (balance.py:45-52)
     def class_hist(self, label_local, class_num=None, ignore_label=None):
         """(c+1,) int64: per-class pixel counts and the valid count over the GLOBAL batch: local histogram ->
