@@ -54,6 +54,23 @@ def main():
         c = rel[:, i]
         print("%-24s min %6.2f  median %6.2f  p95 %6.2f  max %6.2f us" % (nm, c.min(), np.median(c), np.percentile(c, 95), c.max()))
     life = rel[:, 6] - rel[:, 0]
+    smid = t[:, 7]
+    # where does the spread come from?  per-SM means (3 CTAs share an SM), per image, per strip
+    by_sm = {}
+    for sm, lf in zip(smid, life):
+        by_sm.setdefault(int(sm), []).append(lf)
+    sm_mean = np.array([np.mean(v) for v in by_sm.values()])
+    within = np.mean([np.max(v) - np.min(v) for v in by_sm.values() if len(v) > 1])
+    print("per-SM mean lifetime: min %.2f max %.2f std %.2f us; mean spread WITHIN an SM %.2f us; SMs used %d" % (
+        sm_mean.min(), sm_mean.max(), sm_mean.std(), within, len(by_sm)))
+    n = len(life)
+    img = (np.arange(n) * wl.b // n)
+    print("per-image mean lifetime:", " ".join("%.1f" % life[img == i].mean() for i in range(wl.b)))
+    order = np.argsort(life)
+    print("slowest 12 CTAs (blockIdx, smid, us):", [(int(i), int(smid[i]), round(float(life[i]), 1)) for i in order[-12:]])
+    print("fastest 12 CTAs (blockIdx, smid, us):", [(int(i), int(smid[i]), round(float(life[i]), 1)) for i in order[:12]])
+    rows = rel[:, 5] - rel[:, 4]
+    print("corr(lifetime, blockIdx) %.2f; corr(lifetime, smid) %.2f" % (np.corrcoef(life, np.arange(n))[0, 1], np.corrcoef(life, smid)[0, 1]))
     print("CTA lifetime: min %.2f median %.2f max %.2f us; rows phase (first row done -> last row done) median %.2f us" % (
         life.min(), np.median(life), life.max(), np.median(rel[:, 5] - rel[:, 4])))
 

@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict_
     char* const mine = peers.base[rank];
     XHeader* hdr = reinterpret_cast<XHeader*>(mine);
     __shared__ unsigned s_my;
+    // the id-only launch is issued with programmatic stream serialization right behind the region-max kernel (which
+    // releases its dependents at entry): its CTAs are resident by the time that kernel ends, the launch latency is hidden
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
         const unsigned my = *reinterpret_cast<volatile unsigned*>(&hdr->seq_send[slot]) + 1u;
         // peer p must have folded the previous contents of this slot (its ack lands in MY region)
@@ -389,8 +392,16 @@ extern "C" int uem_xchg_send_f32(const void* partials_ws, int b, int c, int k, c
     if (int rc = fill_peers(&P, peer_regions, rank, world, depth, slot, "uem_xchg_send_f32")) return rc;
     const float* partial = (const float*)partials_ws;
     const int* cnt_partial = partial ? (const int*)(partial + (int64_t)b * c * k) : nullptr;
-    xchg_send_kernel<<<dim3((parts & 1) ? kSendChunks : 1, world), 256, 0, (cudaStream_t)stream>>>(partial, cnt_partial, b, c, k, max_id, hist,
-                                                                                                  P, rank, world, slot, global_id_out, parts);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((parts & 1) ? kSendChunks : 1, world, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (parts == 2) ? 1 : 0;   // id only: overlap the launch with the preceding (region-max) kernel
+    UEM_CUDA(cudaLaunchKernelEx(&cfg, xchg_send_kernel, partial, cnt_partial, b, c, k, max_id, hist, P, rank, world, slot, global_id_out, parts));
     UEM_CHECK_LAUNCH();
     return 0;
 }

@@ -76,7 +76,23 @@ struct RefineParams {
     const float* soft;
     float* out;
     unsigned* stats;        // (b, C+2) ordered-u32: per-class max of `out`, -(min of out), bad flag; atomically raised
+    // work split of the persistent column-walk kernels: the grid is n_sm x per_sm CTAs and CTA i is the (i / n_sm)-th CTA
+    // to land on its SM.  The warp scheduler favours the older CTA's warps, so the co-resident CTAs of one SM advance at
+    // different speeds (profiles/r02_refine_cta_timeline_cfg5_by_slot.txt: 88 / 92.5 / 97 us for equal shares, the first
+    // one then leaves its SM a third empty): every CTA gets a share of the rows proportional to slot_w[its slot].
+    int n_sm;
+    float slot_cum[5];      // cumulative, normalised: slot s owns the fraction [slot_cum[s], slot_cum[s+1]) of all rows
 };
+
+// first unit of CTA `bid` (of `grid`) under the per-slot shares; == total * bid / grid for equal shares
+__device__ __forceinline__ int64_t refine_range_begin(const RefineParams& p, int64_t total, int bid, int grid) {
+    if (p.n_sm <= 0 || grid % p.n_sm != 0 || grid / p.n_sm > 4) return total * bid / grid;
+    if (bid >= grid) return total;
+    const int slot = bid / p.n_sm, j = bid - slot * p.n_sm;
+    const double f = (double)p.slot_cum[slot] + ((double)p.slot_cum[slot + 1] - (double)p.slot_cum[slot]) * ((double)j / (double)p.n_sm);
+    int64_t u = (int64_t)(f * (double)total);
+    return u < 0 ? 0 : (u > total ? total : u);
+}
 
 // packed variant over PC class pairs
 template <int PC> __device__ __forceinline__ float exp_shifted2(float2 (&z)[PC]) {
@@ -400,6 +416,9 @@ template <int C, int NT, int NS, int VX>
 __global__ void __launch_bounds__(NT, ((VX == 2 ? UEM_REFINE_COL_MINB_VX2 : UEM_REFINE_COL_MINB) * 128) / NT)
 refine_col_kernel(const RefineParams p, const int ncols_max) {
     UEM_T(0);
+#ifdef UEM_REFINE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_refine_t[blockIdx.x][7] = sm_; }
+#endif
     constexpr int CP = Lay<C>::CP, PC = Lay<C>::PC, NW = NT / 32, WC = 32 * VX;
     constexpr int TS = 3 * CP;                                   // floats per (row, low-res column) of the warp's tap scratch
     constexpr uint32_t kPlane = (uint32_t)WC * 4u;               // bytes of one soft plane of a warp row
@@ -419,7 +438,7 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
 
     // flattened (image, strip, row) space, row fastest; this CTA owns [U0, U1)
     const int64_t total = (int64_t)p.b * nstrips * H;
-    const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int64_t U0 = refine_range_begin(p, total, blockIdx.x, gridDim.x), U1 = refine_range_begin(p, total, blockIdx.x + 1, gridDim.x);
     const int n = (int)(U1 - U0);
     if (n <= 0) return;
     const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
@@ -791,7 +810,7 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
     const int tap_buf_floats = 2 * ncols_max * TS;
 
     const int64_t total = (int64_t)p.b * nstrips * H;
-    const int64_t U0 = total * blockIdx.x / gridDim.x, U1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int64_t U0 = refine_range_begin(p, total, blockIdx.x, gridDim.x), U1 = refine_range_begin(p, total, blockIdx.x + 1, gridDim.x);
     const int n = (int)(U1 - U0);
     if (n <= 0) return;
     const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
@@ -1242,6 +1261,24 @@ static int launch_persistent(K kernel, const RefineParams& p, int threads, size_
 #ifndef UEM_REFINE_COL_VX
 #define UEM_REFINE_COL_VX 2
 #endif
+// per-slot shares of the rows (see RefineParams::slot_cum).  Measured speeds of the 1st / 2nd / 3rd CTA of an SM at equal
+// shares: 1 : 0.95 : 0.905 (config 5), 1 : 0.955 : 0.92 (config 2); "refine_slot_skew" (uem_set_option, per mille of the
+// spread between first and last slot, 100 = +-5 %) sets it; default 0 = equal shares.
+static int g_refine_slot_skew = 0;   // measured: the per-slot finish times even out, the launch does not get shorter (r02_kbench_refine_slot_skew.txt)
+static void refine_slot_shares(RefineParams& p, int grid, int per_sm) {
+    p.n_sm = 0;
+    if (per_sm < 2 || per_sm > 4 || grid != sm_count() * per_sm || g_refine_slot_skew == 0) return;
+    p.n_sm = sm_count();
+    float w[4], sum = 0.f;
+    for (int s = 0; s < per_sm; ++s) {
+        w[s] = 1.0f + 0.001f * (float)g_refine_slot_skew * (0.5f - (float)s / (float)(per_sm - 1));   // +skew/2 .. -skew/2
+        sum += w[s];
+    }
+    p.slot_cum[0] = 0.f;
+    for (int s = 0; s < per_sm; ++s) p.slot_cum[s + 1] = p.slot_cum[s] + w[s] / sum;
+    p.slot_cum[per_sm] = 1.0f;
+}
+
 #ifndef UEM_REFINE_COL2_DSM
 #define UEM_REFINE_COL2_DSM 1
 #endif
@@ -1274,6 +1311,7 @@ static int launch_refine_col2(RefineParams p, cudaStream_t st, bool pdl, bool* d
     const int nstrips = (p.W + NT * 2 - 1) / (NT * 2);
     const int64_t total = (int64_t)p.b * nstrips * p.H;
     const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
+    refine_slot_shares(p, grid, per_sm);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(NT, 1, 1);
@@ -1323,6 +1361,7 @@ static int launch_refine_col(RefineParams p, cudaStream_t st, bool pdl, bool* do
     const int nstrips = (p.W + NT * VX - 1) / (NT * VX);
     const int64_t total = (int64_t)p.b * nstrips * p.H;
     const int grid = (int)min(total, (int64_t)sm_count() * per_sm);
+    refine_slot_shares(p, grid, per_sm);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(NT, 1, 1);
@@ -1418,6 +1457,7 @@ extern "C" __attribute__((visibility("default"))) int uem_debug_refine_timing(un
 extern "C" int uem_set_option(const char* name, int value) {
     UEM_REQUIRE(name, "uem_set_option: NULL name");
     if (strcmp(name, "refine_ctas_per_sm") == 0) { g_uem_refine_ctas_per_sm = value; return 0; }
+    if (strcmp(name, "refine_slot_skew") == 0) { g_refine_slot_skew = value; return 0; }
     if (strcmp(name, "region_ctas_per_sm") == 0) { g_uem_region_ctas_per_sm = value; return 0; }
     if (strcmp(name, "proto_ctas_per_sm") == 0) { g_uem_proto_ctas_per_sm = value; return 0; }
     if (strcmp(name, "refine_form") == 0) { g_refine_form = value < 0 ? -1 : (value ? 1 : 0); return 0; }   // -1: back to the default
