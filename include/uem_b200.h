@@ -106,7 +106,13 @@ UEM_API int uem_pseudo_select_f32(const float* mask, const float* cmax, int b, i
  * for the reference's range assert (pseudo_generation.py:71). */
 UEM_API int64_t uem_class_stats_bytes(int b, int c);
 /* development switches (A/B runs, tests): "refine_form" = 0 (pixel-pair packed column walk) | 1 (class-pair packing) |
- * -1 (the library default); the two forms of the fused label_refine kernel agree bit for bit. */
+ * -1 (the library default); the two forms of the fused label_refine kernel agree bit for bit.
+ * "{refine,region,proto}_ctas_per_sm": cap on resident CTAs per SM (0 = occupancy limit; pipelined hosts cap the region-max kernel).
+ * L2 eviction-priority hints (results never change): "l2_stream" (default 1) = maps a step touches exactly once (feature maps,
+ * full-resolution labels, the selection's outputs and its read of the refined map) are evict_first; "l2_last_use" (default 1) =
+ * the refine kernel's reads of soft / ids on the fused chain are evict_first; "l2_region" = 0 | 1 (evict_first, default) | 2
+ * (evict_last) for the region-max kernel's reads of soft / ids on the fused chain; "l2_keep" = 0 (default) | 2 (evict_last) for
+ * the refine kernel's stores of the refined map, which the selection reads next. */
 UEM_API int uem_set_option(const char* name, int value);
 UEM_API int uem_select_entropy_stats_f32(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw,
                                  float cutoff_top, float cutoff_low, int64_t ignore_label, int64_t* out,

@@ -1068,6 +1068,44 @@ def test_refine_kernel_forms_agree(dev, shape):
     assert torch.equal(outs[0][1], outs[1][1]), "class statistics of the two kernel forms differ"
 
 
+def test_l2_hint_options_do_not_change_results(dev):
+    """The L2 eviction-priority hints (uem_set_option l2_*) only steer cache replacement: every output of the fused chain
+    and of the source-side prototype statistics is bit-identical with every combination of them."""
+    from uemda_b200 import _lib, mining, ops
+    from uemda_b200.gast.alignment import DownscaleLabel
+    b, c, H, W, h, w, k = 2, 6, 128, 256, 8, 16, 64
+    g = torch.Generator().manual_seed(77)
+    soft = torch.softmax(torch.randn(b, c, H, W, generator=g) * 3, dim=1).to(dev)
+    sup = torch.randint(0, 53, (b, 1, H, W), generator=g).to(dev)
+    feat = torch.randn(b, k, h, w, generator=g).to(dev)
+    protos = torch.randn(c, k, generator=g).to(dev)
+    p1 = (torch.randn(b, c, h, w, generator=g) * 4).to(dev)
+    p2 = (torch.randn(b, c, h, w, generator=g) * 4).to(dev)
+    label_s = torch.randint(-1, c, (b, H, W), generator=g).to(dev)
+    down = DownscaleLabel(16, c, -1, 0.75)
+    lib = _lib.load()
+    defaults = {"l2_stream": 1, "l2_last_use": 1, "l2_region": 1, "l2_keep": 0}
+    combos = [dict(defaults), {"l2_stream": 0, "l2_last_use": 0, "l2_region": 0, "l2_keep": 0},
+              {"l2_stream": 1, "l2_last_use": 0, "l2_region": 2, "l2_keep": 2}]
+    outs = []
+    try:
+        for combo in combos:
+            for name, v in combo.items():
+                _lib.check(lib.uem_set_option(name.encode(), v))
+            res = mining.refine_select(7, soft, 2.0, feat=feat, prototypes=protos, pred1=p1, pred2=p2, sup=sup,
+                                       select=(0.8, 0.6, -1), uvem=(0.2, 0.7, 4.0))
+            sums, counts = ops.proto_accumulate(feat, down(label_s), c)
+            outs.append([t.clone() for t in res if t is not None] + [sums.clone(), counts.clone()])
+    finally:
+        for name, v in defaults.items():
+            lib.uem_set_option(name.encode(), v)
+    for other in outs[1:]:
+        assert len(other) == len(outs[0])
+        for a, b2 in zip(outs[0], other):
+            bits = torch.int32 if a.dtype == torch.float32 else a.dtype   # bit patterns: NaN-safe
+            assert torch.equal(a.view(bits), b2.view(bits))
+
+
 # ------------------------------------------------------------------------------------ f4: IAST thresholds, sliding windows
 def test_iast_golden_thresholds_and_labels(dev):
     """IAST class-wise percentile thresholds + thresholded labels against the reference's own ias_thresh driven through the

@@ -1,12 +1,12 @@
-export NCCL_DEBUG=WARN
-for N in 2 4 8; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 40 --warmup 10 > gpurun_out/r2_bench_${N}gpu_f.json 2> gpurun_out/r2_bench_${N}gpu_f.err
-echo "${N}gpu rc=$?" >> gpurun_out/r2_scale3.txt; tail -c 200 gpurun_out/r2_bench_${N}gpu_f.err | tr '\n' ' ' >> gpurun_out/r2_scale3.txt
-python -c "
+O=gpurun_out/r2_l2hints2.txt; : > $O
+for v in "l2_region=0" "l2_region=1" "l2_region=2" "l2_region=1 l2_keep=2" "l2_region=1 l2_last_use=0" "l2_stream=0 l2_last_use=0" "l2_region=0" "l2_region=1"; do
+  o=""; for kv in $v; do o="$o --opt $kv"; done
+  timeout 300 python bench.py --steps 40 --warmup 10 --no-extra --no-e2e --no-cpu-baseline --no-parity $o > gpurun_out/tmp.json 2>gpurun_out/tmp.err
+  python -c "
 import json
-d=json.loads([l for l in open('gpurun_out/r2_bench_${N}gpu_f.json') if l.startswith('{')][-1]); print('${N}gpu', round(d['value']), round(d['ms_per_step']*1e3,1), d['impl_detail']['exchange'], d['impl_detail']['exchange_status'], d['kernels_per_step'], 'e2e', round(d['e2e']['value']), json.dumps(d.get('parity'))[:330])" >> gpurun_out/r2_scale3.txt
+d=json.loads([l for l in open('gpurun_out/tmp.json') if l.startswith('{')][-1]); print('bench [$v]', round(d['value']), round(d['ms_per_step']*1e3,1), 'roofline', round(d['roofline']['frac'],3), d['roofline'].get('kernel_ms'))" >> $O 2>&1
 done
-python bench.py --steps 40 --warmup 10 --no-extra --no-e2e --no-cpu-baseline > gpurun_out/tmp.json 2>/dev/null; python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/tmp.json') if l.startswith('{')][-1]); print('1gpu', round(d['value']), round(d['ms_per_step']*1e3,1))" >> gpurun_out/r2_scale3.txt
-cat gpurun_out/r2_scale3.txt
+timeout 300 python tools/l2_probe.py >> $O 2>&1 || exit 1
+timeout 600 ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:"pearson_tma|region_max_smem|refine_col|select_stats" --csv --log-file gpurun_out/r2_l2probe2.csv python tools/l2_probe.py >> $O 2>&1
+grep -c "pass" gpurun_out/r2_l2probe2.csv >> $O
+cat $O

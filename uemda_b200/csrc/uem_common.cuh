@@ -15,6 +15,14 @@ int uem_fail(const char* fmt, ...);
 // tuning knobs set through uem_set_option (0 = the kernel's own choice); see uem_api.cu
 extern int g_uem_refine_ctas_per_sm;   // cap on resident CTAs per SM of the fused refine kernel (co-residency with the next batch's streaming kernels)
 extern int g_uem_region_ctas_per_sm;   // same for the region-max kernel
+extern int g_uem_l2_stream;            // 1: maps a step reads or writes exactly once carry an L2 evict_first hint, so that they do not push
+                                       // out what the next kernel of the chain re-reads (soft labels + ids: region max -> refine;
+                                       // refined labels: refine -> selection)
+extern int g_uem_l2_keep;              // hint of the refined map between the refine kernel and the selection: 0 = default priority, 2 = evict_last
+extern int g_uem_l2_region;            // hint of the region-max kernel's reads of soft / ids on the fused chain: 0 | 1 evict_first | 2 evict_last
+                                       // (default 1: the refine kernel is not faster on L2-hot inputs, the selection is, so the
+                                       // refined map is the one thing worth the capacity; profiles/r02_l2_hints.txt)
+extern int g_uem_l2_last_use;          // 1: the refine kernel's reads of soft / ids (their last use in the chain) are evict_first
 extern int g_uem_proto_ctas_per_sm;    // same for the prototype-sum kernel (so that a Pearson CTA fits beside it)
 void uem_note_launches(int n);  // bookkeeping for uem_kernel_launches()
 void uem_take_profile_events(void** start, void** stop);
@@ -85,6 +93,45 @@ __device__ __forceinline__ void stg_f4(float* p, float4 v) {
 __device__ __forceinline__ void stg_i64x2(int64_t* p, int64_t a, int64_t b) {
     asm volatile("st.global.v2.s64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
+// ---- the same with an L2 eviction-priority hint (createpolicy handle in a register; kind 0 = evict_normal = no hint)
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    uint64_t pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_f1(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void ldg_i64x2(const int64_t* p, int64_t& a, int64_t& b, uint64_t pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s64 {%0,%1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ int64_t ldg_i64(const int64_t* p, uint64_t pol) {
+    int64_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_f4(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_f1(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_i64x2(int64_t* p, int64_t a, int64_t b, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.s64 [%0], {%1,%2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_i64(int64_t* p, int64_t a, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.s64 [%0], %1, %2;" ::"l"(p), "l"(a), "l"(pol) : "memory");
+}
 // L2-coherent (skips L1) scalar load: used by test-then-atomic on tables other CTAs update
 __device__ __forceinline__ unsigned ld_cg_u32(const unsigned* p) {
     unsigned r;
@@ -97,6 +144,10 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, uint64_t pol) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -105,12 +156,16 @@ template <int VEC> struct PixVec;
 template <> struct PixVec<4> {
     float v[4];
     __device__ __forceinline__ void load(const float* p) { float4 t = ldg_f4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    __device__ __forceinline__ void load(const float* p, uint64_t pol) { float4 t = ldg_f4(p, pol); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void store(float* p) const { stg_f4(p, make_float4(v[0], v[1], v[2], v[3])); }
+    __device__ __forceinline__ void store(float* p, uint64_t pol) const { stg_f4(p, make_float4(v[0], v[1], v[2], v[3]), pol); }
 };
 template <> struct PixVec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float* p) { v[0] = ldg_f1(p); }
+    __device__ __forceinline__ void load(const float* p, uint64_t pol) { v[0] = ldg_f1(p, pol); }
     __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+    __device__ __forceinline__ void store(float* p, uint64_t pol) const { stg_f1(p, v[0], pol); }
 };
 template <int VEC> __device__ __forceinline__ void load_ids(const int64_t* p, int64_t (&id)[VEC]);
 template <> __device__ __forceinline__ void load_ids<4>(const int64_t* p, int64_t (&id)[4]) {
@@ -118,6 +173,18 @@ template <> __device__ __forceinline__ void load_ids<4>(const int64_t* p, int64_
     ldg_i64x2(p + 2, id[2], id[3]);
 }
 template <> __device__ __forceinline__ void load_ids<1>(const int64_t* p, int64_t (&id)[1]) { id[0] = ldg_i64(p); }
+template <int VEC> __device__ __forceinline__ void load_ids(const int64_t* p, int64_t (&id)[VEC], uint64_t pol);
+template <> __device__ __forceinline__ void load_ids<4>(const int64_t* p, int64_t (&id)[4], uint64_t pol) {
+    ldg_i64x2(p, id[0], id[1], pol);
+    ldg_i64x2(p + 2, id[2], id[3], pol);
+}
+template <> __device__ __forceinline__ void load_ids<1>(const int64_t* p, int64_t (&id)[1], uint64_t pol) { id[0] = ldg_i64(p, pol); }
+template <int VEC> __device__ __forceinline__ void store_ids(int64_t* p, const int64_t (&id)[VEC], uint64_t pol);
+template <> __device__ __forceinline__ void store_ids<4>(int64_t* p, const int64_t (&id)[4], uint64_t pol) {
+    stg_i64x2(p, id[0], id[1], pol);
+    stg_i64x2(p + 2, id[2], id[3], pol);
+}
+template <> __device__ __forceinline__ void store_ids<1>(int64_t* p, const int64_t (&id)[1], uint64_t pol) { stg_i64(p, id[0], pol); }
 template <int VEC> __device__ __forceinline__ void store_ids(int64_t* p, const int64_t (&id)[VEC]);
 template <> __device__ __forceinline__ void store_ids<4>(int64_t* p, const int64_t (&id)[4]) {
     stg_i64x2(p, id[0], id[1]);

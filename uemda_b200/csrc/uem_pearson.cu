@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
                                                                   int k, int hw, int kper, int KS, const float* __restrict__ pc,
                                                                   const float* __restrict__ stats, float eps, int reciprocal,
                                                                   float* __restrict__ gpart, int* __restrict__ arrivals,
-                                                                  float* __restrict__ out) {
+                                                                  float* __restrict__ out, int l2_feat) {
     constexpr int NA = 2 + M;
     extern __shared__ __align__(128) unsigned char smem_p[];
     float* tiles = reinterpret_cast<float*>(smem_p);                                   // [kStages][kKT][kPT]
@@ -246,13 +246,14 @@ __global__ void __launch_bounds__(kTmaThreads) pearson_tma_kernel(const __grid_c
         // ---- producer warp: one lane streams the tiles of this CTA's channel range
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
+            const uint64_t pol = l2_policy(l2_feat);   // the feature map is read once: evict_first keeps it from displacing the label maps
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kStages, r = t / kStages;
                 if (r > 0) mbar_wait(&empty[s], (uint32_t)(r - 1) & 1u);
                 const int kk0 = kbeg + t * kKT;
                 const uint32_t pc_bytes = (uint32_t)min(kKT, k - kk0) * kPcStride * 4u;  // the tile's rows of the (k,8) table
                 mbar_arrive_expect_tx(&full[s], kKT * kPT * 4 + pc_bytes);
-                tma_load_3d(tiles + (size_t)s * kKT * kPT, &tmap, px0, kk0, bi, &full[s]);
+                tma_load_3d(tiles + (size_t)s * kKT * kPT, &tmap, px0, kk0, bi, &full[s], pol);
                 tma_load_1d(pcs + (size_t)s * kKT * kPcStride, pc + (int64_t)kk0 * kPcStride, pc_bytes, &full[s]);
             }
         }
@@ -459,7 +460,7 @@ extern "C" int uem_pearson_dist_nchw_f32(const float* feat, int b, int k, int64_
             const size_t smem = (size_t)kStages * (kKT * kPT + kKT * kPcStride) * 4 + 2 * kStages * 8 + (size_t)kPT * (2 + C) * 4;
             UEM_CUDA(cudaFuncSetAttribute(pearson_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pearson_tma_kernel<C><<<dim3(ptiles * KS, b), kTmaThreads, smem, st>>>(tmap, feat, k, (int)hw, kper, KS, pc, stats, eps, reciprocal,
-                                                                                   gpart, arrivals, out);
+                                                                                   gpart, arrivals, out, g_uem_l2_stream ? 1 : 0);
         } else if (vec) {
             dim3 grid(uem_div_up(hw, kPxLanes * 4), b);
             pearson_nchw_kernel<C, 4><<<grid, kPearsonThreads, 0, st>>>(feat, k, hw, pc, stats, eps, reciprocal, out);

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(512) downscale_kernel(const int64_t* __restric
 template <int C, int BR>
 __device__ __forceinline__ void downscale_pow2_body(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
                                                     int64_t cells, int64_t ignore_label, float min_ratio,
-                                                    int64_t* __restrict__ out, int32_t* __restrict__ status) {
+                                                    int64_t* __restrict__ out, int32_t* __restrict__ status, int l2_in) {
+    const uint64_t pol = l2_policy(l2_in);   // the full-resolution labels are read once
     const int tpc = s >> 1;  // lanes per cell (1..32)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t cell = gid / tpc;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void downscale_pow2_body(const int64_t* __restrict__ 
             int64_t a[BR], c2[BR];
 #pragma unroll
             for (int r = 0; r < BR; ++r)
-                if (r0 + r < s) ldg_i64x2(base + (int64_t)(r0 + r) * W, a[r], c2[r]);
+                if (r0 + r < s) ldg_i64x2(base + (int64_t)(r0 + r) * W, a[r], c2[r], pol);
 #pragma unroll
             for (int r = 0; r < BR; ++r)
                 if (r0 + r < s) { add(a[r]); add(c2[r]); }
@@ -150,14 +151,14 @@ __device__ __forceinline__ void downscale_pow2_body(const int64_t* __restrict__ 
 template <int C>
 __global__ void __launch_bounds__(256) downscale_pow2_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h, int w,
                                                              int64_t cells, int64_t ignore_label, float min_ratio,
-                                                             int64_t* __restrict__ out, int32_t* __restrict__ status) {
-    downscale_pow2_body<C, 16>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status);
+                                                             int64_t* __restrict__ out, int32_t* __restrict__ status, int l2_in) {
+    downscale_pow2_body<C, 16>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status, l2_in);
 }
 template <int C>
 __global__ void __launch_bounds__(256, 3) downscale_pow2_stream_kernel(const int64_t* __restrict__ label, int H, int W, int s, int h,
                                                                        int w, int64_t cells, int64_t ignore_label, float min_ratio,
-                                                                       int64_t* __restrict__ out, int32_t* __restrict__ status) {
-    downscale_pow2_body<C, 8>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status);
+                                                                       int64_t* __restrict__ out, int32_t* __restrict__ status, int l2_in) {
+    downscale_pow2_body<C, 8>(label, H, W, s, h, w, cells, ignore_label, min_ratio, out, status, l2_in);
 }
 
 // ------------------------------------------------------------------------------- prototype sums
@@ -360,7 +361,8 @@ struct ProtoTma {
 template <int C, int RW>
 __global__ void __launch_bounds__(kTmaThreads) proto_accum_tma_kernel(const __grid_constant__ CUtensorMap tmap, int k, int hw, int b,
                                                                       const int64_t* __restrict__ label, int64_t ignore_label,
-                                                                      float* __restrict__ partial, int* __restrict__ cnt_partial) {
+                                                                      float* __restrict__ partial, int* __restrict__ cnt_partial,
+                                                                      int l2_feat) {
     using P = ProtoTma<C, RW>;
     extern __shared__ __align__(128) unsigned char smem_q[];
     float* tiles = reinterpret_cast<float*>(smem_q);                                              // [STAGES][ROWS][128]
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(kTmaThreads) proto_accum_tma_kernel(const __gr
     uint32_t T = 0;  // tiles handled so far by this CTA (ring position), same sequence on both sides
     if (warp == kTmaConsumers / 32) {
         if (lane == 0) tma_prefetch_desc(&tmap);
+        const uint64_t pol = l2_policy(l2_feat);   // the feature map is read once
         // the labels of the NEXT tile are fetched while the current one waits for its ring slot, so the label round trip
         // never sits between two TMA issues
         auto fetch_labels = [&](int item, int t, int64_t (&l)[4]) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(kTmaThreads) proto_accum_tma_kernel(const __gr
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive_expect_tx(&full[s], P::TILE_BYTES);
-                    tma_load_3d(tiles + (size_t)s * P::ROWS * kTilePx, &tmap, t * kTilePx, kb * P::ROWS, bi, &full[s]);
+                    tma_load_3d(tiles + (size_t)s * P::ROWS * kTilePx, &tmap, t * kTilePx, kb * P::ROWS, bi, &full[s], pol);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) l[i] = ln[i];
@@ -590,9 +593,9 @@ extern "C" int uem_downscale_label_i64(const int64_t* label, int b, int H, int W
         UEM_DISPATCH_C(n_classes, {
             const int nblk = uem_div_up(threads, 256);
             if (nblk <= 2 * UEM_SMS)
-                downscale_pow2_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status);
+                downscale_pow2_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status, g_uem_l2_stream ? 1 : 0);
             else
-                downscale_pow2_stream_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status);
+                downscale_pow2_stream_kernel<C><<<nblk, 256, 0, st>>>(label, H, W, scale, h, w, cells, ignore_label, min_ratio, out, status, g_uem_l2_stream ? 1 : 0);
         });
         UEM_CHECK_LAUNCH();
         return 0;
@@ -647,7 +650,7 @@ extern "C" int uem_proto_accum_nchw_f32(const float* feat, int b, int k, int64_t
             const int total = b * uem_div_up(k, P::ROWS);
             const int nblk = min(total, UEM_SMS * per_sm);
             proto_accum_tma_kernel<C, UEM_PROTO_RW><<<nblk, kTmaThreads, P::SMEM, st>>>(tmap, k, (int)hw, b, label, ignore_label, partial,
-                                                                                         cnt_partial);
+                                                                                         cnt_partial, g_uem_l2_stream ? 1 : 0);
         } else if (vec) {
             const int tile_px = (int)min((int64_t)kMaskTile, ((hw + 3) / 4) * 4);
             const size_t smem_r = (size_t)C * tile_px * 4 + (size_t)kRing * kChPerWarp * kAccThreads * 16;

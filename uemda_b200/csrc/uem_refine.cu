@@ -80,6 +80,7 @@ struct RefineParams {
     // to land on its SM.  The warp scheduler favours the older CTA's warps, so the co-resident CTAs of one SM advance at
     // different speeds (profiles/r02_refine_cta_timeline_cfg5_by_slot.txt: 88 / 92.5 / 97 us for equal shares, the first
     // one then leaves its SM a third empty): every CTA gets a share of the rows proportional to slot_w[its slot].
+    int l2_in, l2_out;      // L2 eviction-priority hints (l2_policy kinds) of the soft / id reads and of the stores of `out`
     int n_sm;
     float slot_cum[5];      // cumulative, normalised: slot s owns the fraction [slot_cum[s], slot_cum[s+1]) of all rows
 };
@@ -446,6 +447,11 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
     // ---- prefetch side.  A row of the warp's WC columns is NCHUNK 16-byte chunks (chunk k sits at byte 16k of the
     // stage: the planes are contiguous, ids follow); lane l copies chunks l, l+32, ... with cp.async.cg 16.
     // The source pointer of each chunk advances by one image row per unit; recomputed when the strip changes.
+    // L2 hints only in the two-column build (c <= 6): the one-column build sits at its register limit, and the batches it
+    // serves at c >= 7 (LoveDA) are larger than L2 anyway
+    constexpr bool HINT = (VX == 2);
+    const uint64_t pol_in = HINT ? l2_policy(p.l2_in) : 0ull;   // last reader of soft / ids on the fused chain: evict_first
+    const uint64_t pol_out = HINT ? l2_policy(p.l2_out) : 0ull;
     const uint32_t wstage_u32 = smem_u32(wstage) + (uint32_t)lane * 16u;
     const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * (4u * VX);
     int ibs = bs0, iy = y0, ibs_cur = -1;
@@ -478,7 +484,11 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
         const uint32_t d = wstage_u32 + (uint32_t)stage * kWarpStage;
 #pragma unroll
         for (int q = 0; q < NCP; ++q) {
-            if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            if constexpr (HINT) {
+                if (cvalid[q]) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 512u * q), "l"(csrc[q]), "l"(pol_in) : "memory");
+            } else {
+                if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            }
             csrc[q] += cstride[q];
         }
         if (++iy == H) { iy = 0; ++ibs; }
@@ -721,7 +731,8 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
                 float* dst = const_cast<float*>(ob + (int64_t)ci * HW) + idx;
-                if constexpr (VX == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[ci][0], o[ci][1]);
+                if constexpr (VX == 2)
+                    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(dst), "f"(o[ci][0]), "f"(o[ci][1]), "l"(pol_out) : "memory");
                 else *dst = o[ci][0];
             }
         }
@@ -816,6 +827,9 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
     const int bs0 = (int)(U0 / H), y0 = (int)(U0 - (int64_t)bs0 * H);
 
     // ---- prefetch side (as in refine_col_kernel): lane l copies 16-byte chunks l, l+32, ... of a warp row
+    constexpr bool HINT = (C <= 6);
+    const uint64_t pol_in = HINT ? l2_policy(p.l2_in) : 0ull;   // last reader of soft / ids on the fused chain: evict_first
+    const uint64_t pol_out = HINT ? l2_policy(p.l2_out) : 0ull;
     const uint32_t wstage_u32 = smem_u32(wstage) + (uint32_t)lane * 16u;
     const uint32_t rd_base = smem_u32(wstage) + (uint32_t)lane * 8u;
     int ibs = bs0, iy = y0, ibs_cur = -1;
@@ -848,7 +862,11 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
         const uint32_t d = wstage_u32 + (uint32_t)stage * kWarpStage;
 #pragma unroll
         for (int q = 0; q < NCP; ++q) {
-            if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            if constexpr (HINT) {
+                if (cvalid[q]) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 512u * q), "l"(csrc[q]), "l"(pol_in) : "memory");
+            } else {
+                if (cvalid[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * q), "l"(csrc[q]) : "memory");
+            }
             csrc[q] += cstride[q];
         }
         if (++iy == H) { iy = 0; ++ibs; }
@@ -1125,7 +1143,9 @@ refine_col2_kernel(const RefineParams p, const int ncols_max) {
                 const float2 ov = UEM_FMUL2(o[ci], inv);
                 cmax[ci] = fmax3(cmax[ci], ov.x, ov.y);
                 cmin = fmin3(cmin, ov.x, ov.y);
-                *reinterpret_cast<float2*>(const_cast<float*>(ob + (int64_t)ci * HW) + idx) = ov;
+                if constexpr (HINT)
+                    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(const_cast<float*>(ob + (int64_t)ci * HW) + idx), "f"(ov.x), "f"(ov.y), "l"(pol_out) : "memory");
+                else *reinterpret_cast<float2*>(const_cast<float*>(ob + (int64_t)ci * HW) + idx) = ov;
             }
         }
         if (it + 1 < n) {   // the next row's region weights: a whole row of work covers their latency
@@ -1413,6 +1433,8 @@ static int launch_refine(int views, const float* simi, const float* pred1, const
     p.div_temp = pow2 ? 0 : 1;
     p.sup = sup; p.sw = sw_ws; p.R = R; p.ignored_id = ignored_id;
     p.soft = soft; p.out = out; p.stats = stats;
+    p.l2_in = (weights_ready && g_uem_l2_last_use) ? 1 : 0;   // on the fused chain this is the last read of soft / ids
+    p.l2_out = g_uem_l2_keep;                                  // the selection reads `out` next
     const bool vec = (W % 4 == 0) && uem_aligned16(soft) && uem_aligned16(out) && (!sup || uem_aligned16(sup));
     // column-walk kernel: any up-sampling ratio, any low-res width
     const bool colwalk = vec && views == (UEM_VIEW_PROTO | UEM_VIEW_PRED | UEM_VIEW_SUP) && p.n_pred == 2;
@@ -1460,6 +1482,10 @@ extern "C" int uem_set_option(const char* name, int value) {
     if (strcmp(name, "refine_slot_skew") == 0) { g_refine_slot_skew = value; return 0; }
     if (strcmp(name, "region_ctas_per_sm") == 0) { g_uem_region_ctas_per_sm = value; return 0; }
     if (strcmp(name, "proto_ctas_per_sm") == 0) { g_uem_proto_ctas_per_sm = value; return 0; }
+    if (strcmp(name, "l2_stream") == 0) { g_uem_l2_stream = value ? 1 : 0; return 0; }
+    if (strcmp(name, "l2_keep") == 0) { g_uem_l2_keep = value == 2 ? 2 : 0; return 0; }
+    if (strcmp(name, "l2_region") == 0) { g_uem_l2_region = (value >= 0 && value <= 2) ? value : 0; return 0; }
+    if (strcmp(name, "l2_last_use") == 0) { g_uem_l2_last_use = value ? 1 : 0; return 0; }
     if (strcmp(name, "refine_form") == 0) { g_refine_form = value < 0 ? -1 : (value ? 1 : 0); return 0; }   // -1: back to the default
     return uem_fail("uem_set_option: unknown option '%s'", name);
 }

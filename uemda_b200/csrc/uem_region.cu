@@ -252,8 +252,9 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* __restrict__ src, int64_t sb, int64_t sc,
                                                                  const int64_t* __restrict__ index, int64_t N, int64_t R,
                                                                  unsigned* __restrict__ table, long long* __restrict__ maxid,
-                                                                 int* __restrict__ status, const RegionTail tail) {
+                                                                 int* __restrict__ status, const RegionTail tail, int l2) {
     constexpr int CP = (C + 3) & ~3;   // private rows are padded to CP words: a probe is CP/4 x LDS.128
+    const uint64_t pol = l2_policy(l2);   // on the fused chain the refine kernel reads both maps again
     extern __shared__ __align__(16) unsigned tab_s[];  // [R][CP] then [R] touched flags
     __shared__ long long smax[32];
     __shared__ int s_last;
@@ -281,12 +282,12 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
     for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
         const int64_t n0 = g * VEC;
         int64_t id[VEC];
-        load_ids<VEC>(idx + n0, id);
+        load_ids<VEC>(idx + n0, id, pol);
         float v[C][VEC];
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) {
             PixVec<VEC> t;
-            t.load(s + n0 + (int64_t)ci * sc);
+            t.load(s + n0 + (int64_t)ci * sc, pol);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) v[ci][i] = t.v[i];
         }
@@ -662,10 +663,10 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
         dim3 grid(chunks, b);
         if (vec) {
             if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            region_max_smem_kernel<C, 4><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail);
+            region_max_smem_kernel<C, 4><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0);
         } else {
             if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            region_max_smem_kernel<C, 1><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail);
+            region_max_smem_kernel<C, 1><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0);
         }
     });
     UEM_CHECK_LAUNCH();

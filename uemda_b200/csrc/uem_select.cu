@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) select_stats_kernel(const float* __r
                                                                 int64_t hw, float top, float low, int64_t ignore_label,
                                                                 int64_t* __restrict__ out, int has_uvem, float um, float ut,
                                                                 float uig, float ucl, float ucr, float* __restrict__ entropy,
-                                                                float* __restrict__ weight, int64_t* __restrict__ zero_after) {
+                                                                float* __restrict__ weight, int64_t* __restrict__ zero_after, int l2) {
     __shared__ float thr[C];
     const int bi = blockIdx.y;
     // programmatic dependent launch: the CTAs may already be resident while the refine kernel drains
@@ -174,11 +174,13 @@ __global__ void __launch_bounds__(kThreads) select_stats_kernel(const float* __r
     if constexpr (!EXTRA) {
         select_body<C, VEC>(mk, thr, hw, base, ignore_label, 0, out + (int64_t)bi * hw);
     } else {
+        // last reader of the refined map, only writer of the three outputs: everything here is touched once
+        const uint64_t pol = l2_policy(l2);
         float p[C][VEC];
 #pragma unroll
         for (int ci = 0; ci < C; ++ci) {
             PixVec<VEC> v;
-            v.load(mk + (int64_t)ci * hw + base);
+            v.load(mk + (int64_t)ci * hw + base, pol);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) p[ci][i] = v.v[i];
         }
@@ -200,9 +202,9 @@ __global__ void __launch_bounds__(kThreads) select_stats_kernel(const float* __r
             ev.v[i] = u;
             wv.v[i] = has_uvem ? uvem_weight_dev(u, um, ut, uig, ucl, ucr) : 1.0f;
         }
-        store_ids<VEC>(out + (int64_t)bi * hw + base, lab);
-        if (entropy) ev.store(entropy + (int64_t)bi * hw + base);
-        if (weight) wv.store(weight + (int64_t)bi * hw + base);
+        store_ids<VEC>(out + (int64_t)bi * hw + base, lab, pol);
+        if (entropy) ev.store(entropy + (int64_t)bi * hw + base, pol);
+        if (weight) wv.store(weight + (int64_t)bi * hw + base, pol);
     }
 }
 
@@ -261,24 +263,25 @@ int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats
                 ucr = hu ? uvem[4] : 0.f;
     const bool extra = entropy || weight;
     const unsigned* stats = class_stats;
+    const int l2 = g_uem_l2_stream ? 1 : 0;
     int rc = 0;
     UEM_DISPATCH_C(c, {
         if (vec) {
             dim3 grid(uem_div_up(hw / 4, kThreads), b);
             if (extra)
                 rc = launch_maybe_pdl(select_stats_kernel<C, 4, true>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
-                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after, l2);
             else
                 rc = launch_maybe_pdl(select_stats_kernel<C, 4, false>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
-                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after, l2);
         } else {
             dim3 grid(uem_div_up(hw, kThreads), b);
             if (extra)
                 rc = launch_maybe_pdl(select_stats_kernel<C, 1, true>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
-                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after, l2);
             else
                 rc = launch_maybe_pdl(select_stats_kernel<C, 1, false>, grid, kThreads, st, pdl, mask, stats, hw, cutoff_top, cutoff_low,
-                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after);
+                                      ignore_label, out, hu, um, ut, uig, ucl, ucr, entropy, weight, zero_after, l2);
         }
     });
     if (rc) return rc;
