@@ -339,6 +339,13 @@ class Pipeline:
         self.two_stream = os.environ.get("UEM_BENCH_TWO_STREAM", "1") == "1"
         self.split_fold = os.environ.get("UEM_BENCH_SPLIT_FOLD", "0") == "1"
         self.ahead_stream = self.br_proto
+        # development knob: the selection of step i as its own graph on a third stream, so that the refine kernel of step i+1
+        # does not queue behind it (they are independent)
+        self.split_select = os.environ.get("UEM_BENCH_SELECT_STREAM", "0") == "1" and self.two_stream
+        self.sel_stream = torch.cuda.Stream(device=dev, priority=hi if os.environ.get("UEM_BENCH_SEL_PRIO", "l") == "h" else lo)
+        self.refined = [None] * self.n
+        self.ev_s = [torch.cuda.Event() for _ in range(self.n)]
+        self.graphs_s = None
         self.ev_m = [torch.cuda.Event() for _ in range(self.n)]
         self.ev_a = [torch.cuda.Event() for _ in range(self.n)]
         self.graphs_a = None
@@ -384,6 +391,17 @@ class Pipeline:
 
     def ignored_of(self, j):
         return self.ignored[j] if self.peer is not None else self.local_ids[j]   # one rank: the local max id is the global one
+
+    def refine_only_part(self, j):
+        s = self.sets[j]
+        self.refined[j], _ = self.mining.refine_select(7, s["soft"], TEMP, feat=s["feat"], prototypes=self.proto_state, pred1=s["pred1"],
+                                                       pred2=s["pred2"], sup=s["sup"], num_regions=self.R, ignored_id=self.ignored_of(j),
+                                                       eps=self.al.eps, select=None, ws=self.ws[j], regions_ready=True, simi_ready=True)
+
+    def select_part(self, j):
+        r = self.refined[j]
+        hard, ent, wgt = self.ops.pseudo_select_stats(r, r._uem_stats.stats, CUTOFF[0], CUTOFF[1], -1, uvem=UVEM)
+        self.outs[j] = (r, hard, ent, wgt)
 
     def refine_part(self, j):
         s = self.sets[j]
@@ -494,7 +512,7 @@ class Pipeline:
             return False
         try:
             # capturing records the launches without running them: the exchange sequence numbers do not move
-            graphs, graphs_a = [], []
+            graphs, graphs_a, graphs_s = [], [], []
             for j in range(self.n):
                 g = torch.cuda.CUDAGraph()
                 if self.two_stream:
@@ -503,12 +521,20 @@ class Pipeline:
                         self.ahead_body(j)
                     graphs_a.append(ga)
                     with torch.cuda.graph(g, stream=self.main):
-                        self.refine_part(j)
+                        if self.split_select:
+                            self.refine_only_part(j)
+                        else:
+                            self.refine_part(j)
+                    if self.split_select:
+                        gs = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gs, stream=self.sel_stream):
+                            self.select_part(j)
+                        graphs_s.append(gs)
                 else:
                     with torch.cuda.graph(g, stream=self.main):
                         self.step_body(j)
                 graphs.append(g)
-            self.graphs, self.graphs_a = graphs, graphs_a
+            self.graphs, self.graphs_a, self.graphs_s = graphs, graphs_a, graphs_s
             return True
         except Exception as e:  # noqa: BLE001
             print("graph capture failed, timing eagerly: %r" % (e,), file=sys.stderr)
@@ -520,22 +546,31 @@ class Pipeline:
         """the next `cnt` steps of the sequence on the main stream; returns the set index of the last one"""
         j = None
         if self.two_stream and self.graphs is not None and not eager and not serial:
-            sa, sm = self.ahead_stream, self.main
+            sa, sm, ss = self.ahead_stream, self.main, self.sel_stream
             sa.wait_stream(sm)            # whatever ran before (eager steps on the main stream) is ordered before this burst
-            for e in self.ev_m + self.ev_a:
+            ss.wait_stream(sm)
+            for e in self.ev_m + self.ev_a + self.ev_s:
                 e.record(sm)
             for _ in range(cnt):
                 j = self.pos % self.n
                 with torch.cuda.stream(sa):
                     sa.wait_event(self.ev_m[(j + 1) % self.n])     # M(i-2): last reader of the buffers A(i) refills (n = 3)
+                    if self.split_select:
+                        sa.wait_event(self.ev_s[(j + 1) % self.n])
                     self.graphs_a[j].replay()
                     self.ev_a[j].record(sa)
                 with torch.cuda.stream(sm):
                     sm.wait_event(self.ev_a[(j - 1) % self.n])     # A(i-1) prepared set j
                     self.graphs[j].replay()
                     self.ev_m[j].record(sm)
+                if self.split_select:
+                    with torch.cuda.stream(ss):
+                        ss.wait_event(self.ev_m[j])
+                        self.graphs_s[j].replay()
+                        self.ev_s[j].record(ss)
                 self.pos += 1
-            sm.wait_stream(sa)            # the burst ends when both streams are done
+            sm.wait_stream(sa)            # the burst ends when all streams are done
+            sm.wait_stream(ss)
             return j
         with torch.cuda.stream(self.main):
             for _ in range(cnt):
