@@ -41,6 +41,9 @@ int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats
 #define UEM_FMUL2(a, b) __fmul2_rn(a, b)
 #define UEM_FADD2(a, b) __fadd2_rn(a, b)
 
+#ifndef UEM_ABL
+#define UEM_ABL 0   // development: ablation bits of refine_col_kernel (1 no stores, 2 no arithmetic, 4 no gather, 8 one setup, 16 no row loads)
+#endif
 namespace {
 
 constexpr int kRefineThreads = 128;
@@ -461,6 +464,9 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
 #pragma unroll
     for (int q = 0; q < NCP; ++q) { csrc[q] = nullptr; cstride[q] = 0; cvalid[q] = false; }
     auto prefetch = [&](int stage) {
+#if (UEM_ABL & 16)
+        if (stage >= 0) { if (++iy == H) { iy = 0; ++ibs; } return; }   // ablation: rows are whatever the stages hold
+#endif
         if (ibs != ibs_cur) {
             const int bi = ibs / nstrips, s = ibs - bi * nstrips;
             const int xw = s * NT * VX + wid * WC;
@@ -573,7 +579,11 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
             cur_i0 = -1;
         }
         const Lerp ly = make_lerp(y, h, p.sy);
+#if (UEM_ABL & 8)
+        if (ly.i0 != cur_i0 && it == 0) {   // ablation: only the first setup of a CTA
+#else
         if (ly.i0 != cur_i0) {
+#endif
             // new low-res row pair.  The warp's WC columns span `ncols` low-res columns: their 2 x ncols x 3C values are
             // fetched once per warp (lane -> (map, class)), pre-scaled by log2 e [/temp], and every lane then reads the
             // four corners of each of its columns as 128-bit shared-memory loads and interpolates horizontally, once.
@@ -653,7 +663,11 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
                 const uint32_t r = in_region ? lo : Ru;
                 const float4* wp = swb + r * (uint32_t)(CP / 4);
 #pragma unroll
+#if (UEM_ABL & 4)
+                for (int q = 0; q < CP / 4; ++q) swv[v][q] = make_float4(1.f, 1.f, 1.f, __uint_as_float(0x3f800000u + (r & 1u)));
+#else
                 for (int q = 0; q < CP / 4; ++q) swv[v][q] = ldg_f4_l1(wp + q);
+#endif
             }
             float sv[C][VX];
 #pragma unroll
@@ -667,6 +681,18 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
             float o[C][VX];
 #pragma unroll
             for (int v = 0; v < VX; ++v) {
+#if (UEM_ABL & 2)
+                {   // ablation: no arithmetic (loads, gather, stores and statistics stay)
+#pragma unroll
+                    for (int ci = 0; ci < C; ++ci) {
+                        const float ov = sv[ci][v] * swv[v][ci / 4].x + t2.x * A[v][ci % 3][0].x;
+                        o[ci][v] = ov;
+                        cmax[ci] = fmaxf(cmax[ci], ov);
+                        cmin = fminf(cmin, ov);
+                    }
+                    continue;
+                }
+#endif
                 float2 wgt2[PC];
                 {   // prototype view: softmax(T=1) of the up-sampled 1/distance, / (max + 1e-7) == e_c * (1 - 1e-7 S)
                     float2 z[PC];
@@ -731,6 +757,9 @@ refine_col_kernel(const RefineParams p, const int ncols_max) {
 #pragma unroll
             for (int ci = 0; ci < C; ++ci) {
                 float* dst = const_cast<float*>(ob + (int64_t)ci * HW) + idx;
+#if (UEM_ABL & 1)
+                if (o[ci][0] != 12345.678f) continue;   // ablation: no stores (the values stay live through the statistics)
+#endif
                 if constexpr (VX == 2)
                     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(dst), "f"(o[ci][0]), "f"(o[ci][1]), "l"(pol_out) : "memory");
                 else *dst = o[ci][0];
