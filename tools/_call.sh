@@ -1,13 +1,8 @@
-O=gpurun_out/r2_refine_ablation.txt; : > $O
-for v in 0 1 2 4 8 16 3 18 19; do
-  if [ $v = 0 ]; then L=uemda_b200/libuem_b200.so; else L=uemda_b200/libuem_b200_abl$v.so; fi
-  echo "== UEM_ABL=$v" >> $O
-  UEM_B200_LIB=$PWD/$L timeout 200 python tools/kbench.py --only label_refine >> $O 2>&1
-done
-echo "== cfg5 (batch 32)" >> $O
-for v in 0 1 2 3 19; do
-  if [ $v = 0 ]; then L=uemda_b200/libuem_b200.so; else L=uemda_b200/libuem_b200_abl$v.so; fi
-  echo "== UEM_ABL=$v" >> $O
-  UEM_B200_LIB=$PWD/$L timeout 200 python tools/kbench.py --workload cfg5_sweep_32x6x512 --iters 24 --only label_refine >> $O 2>&1
-done
-grep -v "^entry" $O
+O=gpurun_out/r2_final1.txt; : > $O
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 >> $O
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> $O 2>&1
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_final_1gpu.json 2> gpurun_out/bench_r02_final_1gpu.err; echo "bench rc=$?" >> $O
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_final_ref.json 2> gpurun_out/bench_r02_final_ref.err; echo "ref rc=$?" >> $O
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_c.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline --no-parity > gpurun_out/ncu_c.log 2>&1; echo "ncu rc=$?" >> $O
+tail -c 600 gpurun_out/bench_r02_final_1gpu.err >> $O
+cat $O
