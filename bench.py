@@ -338,6 +338,11 @@ class Pipeline:
         # step's tail overlaps the next step's head instead of one drain per step: M(i) waits for A(i-1), A(i) for M(i-2)
         self.two_stream = os.environ.get("UEM_BENCH_TWO_STREAM", "1") == "1"
         self.split_fold = os.environ.get("UEM_BENCH_SPLIT_FOLD", "0") == "1"
+        # early_send: a step's prototype sums leave for the peers right behind the kernel that produced them (one step before
+        # their consumer, the fold + EMA launch), so no rank ever waits for a peer that is a few microseconds behind
+        self.early_send = os.environ.get("UEM_BENCH_EARLY_SEND", "0") == "1"
+        # region_send: the id part of a step's send rides in the last CTA of the region-max kernel (no launch of its own)
+        self.region_send = os.environ.get("UEM_BENCH_REGION_SEND", "1") == "1"
         self.ahead_stream = self.br_proto
         # development knob: the selection of step i as its own graph on a third stream, so that the refine kernel of step i+1
         # does not queue behind it (they are independent)
@@ -361,23 +366,32 @@ class Pipeline:
     def region_part(self, j):
         """region maxima of target batch j -> superpixel-view weights + the rank-local max id (alignment.py:238-253)"""
         s = self.sets[j]
-        self.local_ids[j] = self.mining.region_phase(s["soft"], s["sup"], TEMP, self.R, self.ws[j], self.wl.h, self.wl.w, self.wl.k)
+        xc = (self.peer, j % self.peer.depth, self.ignored[j]) if (self.peer is not None and self.region_send) else None
+        self.local_ids[j] = self.mining.region_phase(s["soft"], s["sup"], TEMP, self.R, self.ws[j], self.wl.h, self.wl.w, self.wl.k,
+                                                     exchange=xc)
 
     def send_id_part(self, j):
         """N > 1: this rank's max id of step j into every rank's slot, right behind the region pass (one step ahead of its
         consumer); the same launch polls the other ranks' ids and leaves the batch-global ignored id (alignment.py:241)."""
-        if self.peer is not None:
+        if self.peer is not None and not self.region_send:
             self.miner.send_stats(None, self.local_ids[j], j % self.peer.depth, global_id_out=self.ignored[j], part="id")
 
     def send_sums_part(self, j):
         """N > 1: prototype sums / counts of step j, at the head of step j's own Pearson branch: not at the tail of a graph.
         Merged into the fold + EMA launch (ema_part) unless UEM_BENCH_SPLIT_FOLD=1."""
-        if self.peer is not None and self.split_fold:
+        if self.peer is not None and self.split_fold and not self.early_send:
+            self.miner.send_stats(self.partials[j], None, j % self.peer.depth, part="sums")
+
+    def send_sums_early(self, j):
+        """N > 1, UEM_BENCH_EARLY_SEND=1: the sums of step j right behind source_part(j), i.e. one step ahead of ema_part(j).
+        The caller orders it behind send_id_part(j): both tag their words with the slot's current sequence number and
+        this one, the final send of the step, advances it."""
+        if self.peer is not None and self.early_send:
             self.miner.send_stats(self.partials[j], None, j % self.peer.depth, part="sums")
 
     def ema_part(self, j):
         """prototype EMA of step j (alignment.py:347-353): its last reader (the Pearson pass of step j) ran one step earlier"""
-        if self.peer is not None and self.split_fold:
+        if self.peer is not None and (self.split_fold or self.early_send):
             self.miner.apply_peer(j % self.peer.depth, in_place=True)
         elif self.peer is not None:
             self.miner.exchange_apply(self.partials[j], j % self.peer.depth, in_place=True)   # send + poll + fold + EMA
@@ -428,6 +442,7 @@ class Pipeline:
             self.region_part(jn)
             self.send_id_part(jn)
             self.source_part(jn)
+            self.send_sums_early(jn)
             return
         if self.two_stream:
             self.ahead_body(j)
@@ -435,11 +450,14 @@ class Pipeline:
             return
         for st in (self.br_region, self.br_source, self.br_proto):
             st.wait_stream(cur)
-        with torch.cuda.stream(self.br_source):
-            self.source_part(jn)
         with torch.cuda.stream(self.br_region):
             self.region_part(jn)
             self.send_id_part(jn)
+        with torch.cuda.stream(self.br_source):
+            self.source_part(jn)
+            if self.peer is not None and self.early_send:
+                self.br_source.wait_stream(self.br_region)
+                self.send_sums_early(jn)
         with torch.cuda.stream(self.br_proto):
             self.send_sums_part(j)
             self.ema_part(j)
@@ -455,11 +473,14 @@ class Pipeline:
         jn = (j + 1) % self.n
         self.br_region.wait_stream(cur)
         self.br_source.wait_stream(cur)
-        with torch.cuda.stream(self.br_source):
-            self.source_part(jn)
         with torch.cuda.stream(self.br_region):
             self.region_part(jn)
             self.send_id_part(jn)
+        with torch.cuda.stream(self.br_source):
+            self.source_part(jn)
+            if self.peer is not None and self.early_send:
+                self.br_source.wait_stream(self.br_region)   # id before sums: see send_sums_early
+                self.send_sums_early(jn)
         self.send_sums_part(j)
         self.ema_part(j)
         self.proto_part(jn)
@@ -489,6 +510,7 @@ class Pipeline:
                 self.send_id_part(jn)
                 ev[5].record()
                 self.source_part(jn)
+                self.send_sums_early(jn)
                 ev[6].record()
                 self.pos += 1
                 torch.cuda.synchronize()
@@ -504,6 +526,7 @@ class Pipeline:
             self.region_part(0)
             self.source_part(0)
             self.send_id_part(0)
+            self.send_sums_early(0)
         self.main.synchronize()
         self.pos = 0
 

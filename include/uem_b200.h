@@ -196,6 +196,14 @@ UEM_API int64_t uem_mine_ws_stats_offset(int b, int c, int H, int W, int h, int 
 UEM_API int64_t uem_mine_ws_maxid_offset(int b, int c, int H, int W, int h, int w, int k, int64_t R);
 UEM_API int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
                               int w, int k, float temp, void* ws, void* stream);
+/* Same pass, and the last CTA of its region-max kernel also carries the id part of the step's exchange (see
+ * uem_xchg_send_f32 with parts = 2 below: same slot, same sequence number; the sums follow with parts = 5 or inside
+ * uem_xchg_exchange_fold_ema_f32): this rank's max id is stored into slot `slot` of every rank's region and, when
+ * global_id_out is given, the batch-global id (alignment.py:241) is left there once all ranks' ids of this step have
+ * arrived (bounded poll).  peer_regions / rank / world / depth as for uem_xchg_send_f32; the slot geometry uses this call's c, k. */
+UEM_API int uem_mine_region_phase_xchg_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
+                                   int w, int k, float temp, void* ws, const void* const* peer_regions, int rank, int world,
+                                   int depth, int slot, int64_t* global_id_out, void* stream);
 /* The prototype half on its own: 1/Pearson distance of feat (b,k,h,w) to protos (c,k) (alignment.py:215-217) into the
  * similarity slot of ws.  It only depends on the prototype bank, so in a pipelined loop it runs as soon as the EMA of the
  * previous step is done, next to that step's refine / selection kernels; uem_mine_refine_select_f32(views |

@@ -728,6 +728,63 @@ def test_staged_region_phase_equals_fused_chain(dev):
         assert int(local.item()) == 0, "the selection kernel zeroes the max-id slot again"
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_region_phase_carries_the_id_send(dev, world):
+    """8e: the id part of a step's exchange issued by the LAST CTA of the region-max kernel (uem_mine_region_phase_xchg_f32)
+    instead of a launch of its own.  ``world`` ranks emulated on one device, launches issued in an order in which nothing
+    ever has to wait (only the last rank polls: every other id is already there).  Every rank has a different max
+    superpixel id; 5 steps > depth exercise slot reuse and the acknowledgements; the staged chain fed with the exchanged
+    id equals the one-call chain given the same batch-global id."""
+    from uemda_b200 import mining, ops
+    from uemda_b200.exchange import PeerExchange
+    from uemda_b200.synth import WORKLOADS, make_inputs
+    wl = WORKLOADS["tiny"]
+    c, k, depth = wl.c, wl.k, 3
+    xs = PeerExchange.local_only(world, c, k, depth=depth, device=dev)
+    inps = [_to(make_inputs(wl, seed=20 + r), dev) for r in range(world)]
+    R = max(int(i["ignore_id"]) for i in inps) + 1 + world
+    for r, inp in enumerate(inps):   # rank r's largest id is R - 1 - r: the ranks disagree about the max
+        inp["sup"] = torch.where(inp["sup"] == int(inp["ignore_id"]), torch.full_like(inp["sup"], R - 1 - r), inp["sup"])
+    wss = [mining.mine_workspace(inps[r]["soft"], R, wl.h, wl.w, wl.k) for r in range(world)]
+    banks = [inps[0]["prototypes"].clone() for _ in range(world)]
+    gids = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    for step in range(5):
+        slot = step % depth
+        locals_ = []
+        for r in range(world):
+            last = r == world - 1
+            loc = mining.region_phase(inps[r]["soft"], inps[r]["sup"], 2.0, R, wss[r], wl.h, wl.w, wl.k,
+                                      exchange=(xs[r], slot, gids[r] if last else None))
+            locals_.append(int(loc.item()))
+        assert locals_ == [R - 1 - r for r in range(world)]
+        assert int(gids[world - 1]) == R - 1, "batch-global id polled by the region-max kernel's tail"
+        for r in range(world - 1):
+            xs[r].wait_max_id(slot, out=gids[r])
+            assert int(gids[r]) == R - 1
+        # the sums of the step follow with the same sequence number, then the fold acknowledges the slot
+        parts = [ops.proto_accumulate(inps[r]["feat_s"], mining_down(inps[r], wl), c, -1, fold=False) for r in range(world)]
+        for r in range(world):
+            xs[r].send(parts[r], None, slot, part="sums")
+        for r in range(world):
+            xs[r].fold_finalize(slot, banks[r], eps=1e-7, decay=0.9, out=banks[r])
+            assert xs[r].status() == 0
+            assert torch.equal(banks[r], banks[0])
+        # refine + selection of every rank on the staged regions with the exchanged id == the one-call chain given that id
+        for r in range(world):
+            inp = inps[r]
+            kw = dict(feat=inp["feat"], prototypes=inp["prototypes"], pred1=inp["pred1"], pred2=inp["pred2"], sup=inp["sup"],
+                      num_regions=R, select=(0.8, 0.6, -1), uvem=(0.2, 0.7, 4.0))
+            got = mining.refine_select(7, inp["soft"], 2.0, ignored_id=gids[r], ws=wss[r], regions_ready=True, **kw)
+            want = mining.refine_select(7, inp["soft"], 2.0, ignored_id=gids[r].clone(), **kw)
+            for a, b2, name in zip(got, want, ("refined", "hard", "entropy", "uvem weight")):
+                _eq(a, b2, "rank %d staged %s" % (r, name))
+
+
+def mining_down(inp, wl):
+    from uemda_b200.gast.alignment import DownscaleLabel
+    return DownscaleLabel(wl.scale, wl.c, -1, 0.75)(inp["label_s"])
+
+
 def test_pack_from_partials_equals_fold_then_pack(dev):
     """8e: folding the per-image prototype partials and packing them in ONE launch is bit-identical to fold -> pack."""
     from uemda_b200 import ops

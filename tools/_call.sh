@@ -1,8 +1,8 @@
-O=gpurun_out/r2_final1.txt; : > $O
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 >> $O
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> $O 2>&1
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_final_1gpu.json 2> gpurun_out/bench_r02_final_1gpu.err; echo "bench rc=$?" >> $O
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_final_ref.json 2> gpurun_out/bench_r02_final_ref.err; echo "ref rc=$?" >> $O
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_c.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline --no-parity > gpurun_out/ncu_c.log 2>&1; echo "ncu rc=$?" >> $O
-tail -c 600 gpurun_out/bench_r02_final_1gpu.err >> $O
+O=gpurun_out/r2_tests_f.txt; : > $O
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 >> $O
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> $O 2>&1
+timeout 300 python bench.py --steps 40 --warmup 10 --no-extra --no-e2e --no-cpu-baseline --no-parity > gpurun_out/tmp.json 2>gpurun_out/tmp.err
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/tmp.json') if l.startswith('{')][-1]); print('1gpu', round(d['value']), round(d['ms_per_step']*1e3,1))" >> $O
 cat $O

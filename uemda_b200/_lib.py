@@ -54,6 +54,7 @@ SIGNATURES = {
     "uem_mine_ws_stats_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_ws_maxid_offset": (_L, [_I, _I, _I, _I, _I, _I, _I, _L]),
     "uem_mine_region_phase_f32": (_I, [_P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "uem_mine_region_phase_xchg_f32": (_I, [_P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P]),
     "uem_mine_proto_phase_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _L, _F, _P, _P]),
     "uem_mine_refine_select_f32": (_I, [_I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F,
                                         _L, _P, _P, _P, _P, _P, _P, _P]),

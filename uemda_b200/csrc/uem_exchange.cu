@@ -33,82 +33,10 @@
 //   [1280, 1536)         ack_flag[4][16] u32       written by peers
 //   [2048, ...)          slots[depth][world][slot_bytes]
 // slot (8-byte LL words): [c*k sums | pad to 16 B][c counts lo,hi][c+1 hist lo,hi][max id lo,hi]
-#include "uem_common.cuh"
-#include <limits.h>
-#include <stddef.h>
+#include "uem_xchg_dev.cuh"
 #include <string.h>
 
 namespace {
-
-constexpr int kMaxWorld = 16;
-constexpr int kMaxDepth = 4;
-constexpr int kSendChunks = 6;
-constexpr int kOffAcks = 1280, kOffSlots = 2048;
-constexpr unsigned long long kSpinLimitNs = 2000000000ull;
-
-struct XHeader {
-    unsigned seq_send[kMaxDepth];
-    unsigned seq_recv[kMaxDepth];
-    unsigned arrive_all[kMaxDepth];
-    unsigned fold_arrive[kMaxDepth];
-    int status;
-};
-static_assert(sizeof(XHeader) <= kOffAcks, "header overflows its page");
-
-struct Peers {
-    char* base[kMaxWorld];
-};
-
-// slot geometry in 8-byte LL words
-__host__ __device__ inline int64_t sum_words(int c, int k) { return (((int64_t)c * k) + 3) & ~(int64_t)3; }
-__host__ __device__ inline int64_t tail_words(int c) { return (int64_t)(2 * c + 2) * 2; }   // int64 values as (lo, hi)
-__host__ __device__ inline int64_t slot_bytes(int c, int k) { return ((sum_words(c, k) + tail_words(c)) * 8 + 127) & ~(int64_t)127; }
-
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// bounded spin until *flag >= want; returns false on timeout
-__device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned want) {
-    if ((int)(ld_acquire_sys(flag) - want) >= 0) return true;
-    const unsigned long long t0 = globaltimer_ns();
-    while ((int)(ld_acquire_sys(flag) - want) < 0) {
-        __nanosleep(64);
-        if (globaltimer_ns() - t0 > kSpinLimitNs) return false;
-    }
-    return true;
-}
-// LL word: one 8-byte transaction {payload, sequence number}
-__device__ __forceinline__ void ll_store(char* dst, unsigned payload, unsigned seq) {
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(payload), "r"(seq) : "memory");
-}
-// polls (bounded) until the word carries `seq`; *ok = false on timeout
-__device__ __forceinline__ unsigned ll_load(const char* src, unsigned seq, bool* ok) {
-    unsigned v, f;
-    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
-    if (f == seq) return v;
-    const unsigned long long t0 = globaltimer_ns();
-    do {
-        __nanosleep(32);
-        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
-        if (globaltimer_ns() - t0 > kSpinLimitNs) { *ok = false; return v; }
-    } while (f != seq);
-    return v;
-}
-
-__device__ __forceinline__ int64_t ll_load_i64(const char* src, unsigned seq, bool* ok) {
-    const unsigned lo = ll_load(src, seq, ok), hi = ll_load(src + 8, seq, ok);
-    return (int64_t)(((uint64_t)hi << 32) | lo);
-}
 
 __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial, int b,
                                                         int c, int k, const int64_t* __restrict__ max_id,
@@ -236,13 +164,9 @@ __global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers pee
     bool ok = true;
     if (i < ck) {
         const int ci = i / k;
-        float s = 0.f;
-        int64_t n = 0;
-        for (int r = 0; r < world; ++r) {   // rank order: identical on every rank
-            const float v = __uint_as_float(ll_load(slots + r * sb + (int64_t)i * 8, want, &ok));
-            s = r ? s + v : v;
-            n += ll_load_i64(tails + r * sb + (int64_t)ci * 16, want, &ok);
-        }
+        float s;
+        int64_t n;
+        ll_fold_ranks(slots + (int64_t)i * 8, tails + (int64_t)ci * 16, sb, world, want, &s, &n, &ok);   // rank order: identical on every rank
         if (sums_out) sums_out[i] = s;
         if (proto_new) {
             const float old = proto_old[i];
@@ -327,13 +251,9 @@ __global__ void __launch_bounds__(256) xchg_exchange_fold_kernel(const float* __
     bool ok = true;
     if (i < ck) {
         const int ci = i / k;
-        float s = 0.f;
-        int64_t n = 0;
-        for (int r = 0; r < world; ++r) {
-            const float v = __uint_as_float(ll_load(slots + r * sb + (int64_t)i * 8, my, &ok));
-            s = r ? s + v : v;
-            n += ll_load_i64(tails + r * sb + (int64_t)ci * 16, my, &ok);
-        }
+        float s;
+        int64_t n;
+        ll_fold_ranks(slots + (int64_t)i * 8, tails + (int64_t)ci * 16, sb, world, my, &s, &n, &ok);   // rank order
         if (sums_out) sums_out[i] = s;
         if (proto_new) {
             const float old = proto_old[i];
@@ -364,16 +284,6 @@ __global__ void __launch_bounds__(256) xchg_exchange_fold_kernel(const float* __
             *reinterpret_cast<volatile unsigned*>(&hdr->seq_recv[slot]) = my;
         }
     }
-}
-
-int fill_peers(Peers* P, const void* const* peer_regions, int rank, int world, int depth, int slot, const char* who) {
-    UEM_REQUIRE(peer_regions && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "%s: bad rank/world (%d/%d, at most %d ranks)",
-                who, rank, world, kMaxWorld);
-    UEM_REQUIRE(depth >= 1 && depth <= kMaxDepth && slot >= 0 && slot < depth, "%s: bad slot/depth (%d/%d, depth at most %d)", who, slot,
-                depth, kMaxDepth);
-    for (int r = 0; r < kMaxWorld; ++r) P->base[r] = r < world ? (char*)peer_regions[r] : nullptr;
-    for (int r = 0; r < world; ++r) UEM_REQUIRE(P->base[r], "%s: peer region %d is NULL", who, r);
-    return 0;
 }
 
 }  // namespace

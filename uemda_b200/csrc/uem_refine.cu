@@ -33,6 +33,7 @@ int uem_i64_max_accumulate(const int64_t* x, int64_t n, int64_t* out_max, cudaSt
 int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* index, int b, int64_t N, int c, int64_t R,
                        unsigned* table, int64_t* maxid_out, int* status, float* tail_sw, int* tail_done, float temp,
                        unsigned* zero_words, int n_zero, cudaStream_t st);
+int uem_region_arm_xchg(const void* const* peer_regions, int rank, int world, int depth, int slot, int c, int k, int64_t* global_id_out);
 int uem_select_entropy_stats_impl(const float* mask, const uint32_t* class_stats, int b, int c, int64_t hw, float cutoff_top,
                                   float cutoff_low, int64_t ignore_label, int64_t* out, const float* uvem, float* entropy,
                                   float* weight, int64_t* zero_after, int pdl, cudaStream_t st);
@@ -1616,6 +1617,17 @@ extern "C" int uem_mine_region_phase_f32(const int64_t* sup, int64_t R, const fl
     return uem_region_max_f32(soft, (int64_t)c * HW, HW, sup, b, HW, c, R, (unsigned*)(base + L.region), (int64_t*)(base + L.maxid),
                               (int*)base, (float*)(base + L.sw), (int*)(base + L.done), temp, (unsigned*)(base + L.stats), b * (c + 2),
                               (cudaStream_t)stream);
+}
+
+// Same, and the LAST CTA of the region-max kernel also carries the id part of the step's multi-GPU send (uem_exchange.cu):
+// this rank's max id goes into slot `slot` of every rank and, with global_id_out, the batch-global id (alignment.py:241) is
+// left there once every rank's id of this step has arrived -- uem_xchg_send_f32(parts = 2) without a launch of its own.
+extern "C" int uem_mine_region_phase_xchg_f32(const int64_t* sup, int64_t R, const float* soft, int b, int c, int H, int W, int h,
+                                              int w, int k, float temp, void* ws, const void* const* peer_regions, int rank, int world,
+                                              int depth, int slot, int64_t* global_id_out, void* stream) {
+    UEM_REQUIRE(c > 0 && k > 0, "uem_mine_region_phase_xchg_f32: bad arguments");
+    if (int rc = uem_region_arm_xchg(peer_regions, rank, world, depth, slot, c, k, global_id_out)) return rc;
+    return uem_mine_region_phase_f32(sup, R, soft, b, c, H, W, h, w, k, temp, ws, stream);
 }
 
 extern "C" int uem_mine_proto_phase_f32(const float* feat, int k, const float* protos, int b, int c, int H, int W, int h, int w,

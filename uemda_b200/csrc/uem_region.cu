@@ -10,7 +10,7 @@
 //     value would actually raise the slot (a max changes O(log n) times);
 //   * the hot id (after 7x7 edge shrinking ~60 % of all pixels carry the ignore id) is reduced
 //     in registers and flushed once per CTA.
-#include "uem_common.cuh"
+#include "uem_xchg_dev.cuh"
 
 namespace {
 
@@ -252,7 +252,8 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* __restrict__ src, int64_t sb, int64_t sc,
                                                                  const int64_t* __restrict__ index, int64_t N, int64_t R,
                                                                  unsigned* __restrict__ table, long long* __restrict__ maxid,
-                                                                 int* __restrict__ status, const RegionTail tail, int l2) {
+                                                                 int* __restrict__ status, const RegionTail tail, int l2,
+                                                                 const RegionXchg xchg) {
     constexpr int CP = (C + 3) & ~3;   // private rows are padded to CP words: a probe is CP/4 x LDS.128
     const uint64_t pol = l2_policy(l2);   // on the fused chain the refine kernel reads both maps again
     extern __shared__ __align__(16) unsigned tab_s[];  // [R][CP] then [R] touched flags
@@ -333,13 +334,13 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
             if (e > old[ci]) atomicMax(tab + r * C + ci, e);
         }
     }
-    if (tail.sw == nullptr) return;
+    if (tail.sw == nullptr) return;   // (the exchange rides on the fused chain only)
     // ---- last CTA of this image: per-region weights, table rows back to zero
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + bi, 1) == (int)gridDim.x - 1);
     __syncthreads();
-    if (!s_last) return;
+    if (s_last) {
     __threadfence();
     float* swb = tail.sw + (int64_t)bi * (R + 1) * CP;
     for (int r = threadIdx.x; r <= (int)R; r += blockDim.x) {
@@ -366,6 +367,20 @@ __global__ void __launch_bounds__(1024, 1) region_max_smem_kernel(const float* _
         for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     }
     if (threadIdx.x == 0) tail.done[bi] = 0;
+    }
+    if (xchg.world == 0) return;
+    // ---- multi-GPU: the last CTA of the whole launch sends this rank's max id to every rank (and, with global_id_out,
+    // waits for theirs): the id part of the step's exchange without a launch of its own
+    XHeader* xh = reinterpret_cast<XHeader*>(xchg.peers.base[xchg.rank]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&xh->region_done, 1u) == gridDim.x * gridDim.y - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long local_id = *reinterpret_cast<volatile long long*>(maxid);
+    xchg_send_id_from_cta(xchg, local_id);
+    if (threadIdx.x == 0) xh->region_done = 0u;
 }
 
 // decode the slot table into the dense float output torch_scatter returns (untouched -> 0)
@@ -633,6 +648,19 @@ extern "C" int64_t uem_region_reduce_ws_bytes(int b, int64_t R, int c) {
     return ((int64_t)b * R * c + (int64_t)b * R + 4) * 4;
 }
 
+// The id part of a multi-GPU send armed for the NEXT fused region-max launch of this host thread (uem_mine_region_phase_xchg_f32).
+static thread_local RegionXchg g_armed_xchg;
+static thread_local bool g_has_armed_xchg = false;
+int uem_region_arm_xchg(const void* const* peer_regions, int rank, int world, int depth, int slot, int c, int k, int64_t* global_id_out) {
+    RegionXchg x{};
+    if (int rc = fill_peers(&x.peers, peer_regions, rank, world, depth, slot, "uem_mine_region_phase_xchg_f32")) return rc;
+    x.rank = rank; x.world = world; x.slot = slot; x.c = c; x.k = k;
+    x.global_id_out = (long long*)global_id_out;
+    g_armed_xchg = x;
+    g_has_armed_xchg = true;
+    return 0;
+}
+
 // Region maxima of a planar map into the encoded table (zero on entry); optionally the batch max id (maxid_out zero on
 // entry, ids are >= 0) and the fused weight tail (see RegionTail; tail_sw == nullptr: plain reduction).
 // Needs R*c*4 + R bytes of shared memory per CTA.
@@ -650,6 +678,12 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
     int chunks = max(1, (UEM_SMS * per_sm) / b);
     const int64_t groups = N / (vec ? 4 : 1);
     chunks = (int)min((int64_t)chunks, max((int64_t)1, groups / threads));
+    RegionXchg xchg{};
+    if (g_has_armed_xchg) {
+        g_has_armed_xchg = false;
+        UEM_REQUIRE(tail_sw && maxid_out, "uem_region_max_f32: the id send rides on the fused chain's region pass only");
+        xchg = g_armed_xchg;
+    }
     RegionTail tail{};
     tail.sw = tail_sw;
     tail.done = tail_done;
@@ -663,10 +697,10 @@ int uem_region_max_f32(const float* src, int64_t sb, int64_t sc, const int64_t* 
         dim3 grid(chunks, b);
         if (vec) {
             if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            region_max_smem_kernel<C, 4><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0);
+            region_max_smem_kernel<C, 4><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0, xchg);
         } else {
             if (smem > 48 * 1024) UEM_CUDA(cudaFuncSetAttribute(region_max_smem_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            region_max_smem_kernel<C, 1><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0);
+            region_max_smem_kernel<C, 1><<<grid, threads, smem, st>>>(src, sb, sc, index, N, R, table, (long long*)maxid_out, status, tail, tail_sw ? g_uem_l2_region : 0, xchg);
         }
     });
     UEM_CHECK_LAUNCH();

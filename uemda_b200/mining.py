@@ -57,11 +57,13 @@ def mine_workspace(soft, num_regions, h, w, k):
     return torch.zeros(max(int(need), 16), dtype=torch.uint8, device=soft.device)
 
 
-def region_phase(soft, sup, temp, num_regions, ws, h, w, k):
+def region_phase(soft, sup, temp, num_regions, ws, h, w, k, exchange=None):
     """The region half of the chain on its own (multi-GPU form): region maxima of ``soft`` -> superpixel-view weights in
     ``ws``; returns the rank-LOCAL max superpixel id as a (1,) int64 view INTO ``ws`` (read it -- e.g. pack it for the
     exchange -- before the matching ``refine_select(..., regions_ready=True)``, whose selection kernel zeroes the slot).
-    Nothing here needs the batch-global id, so this can run one step ahead of the exchange (alignment.py:241-258)."""
+    Nothing here needs the batch-global id, so this can run one step ahead of the exchange (alignment.py:241-258).
+    exchange: None or (PeerExchange, slot, global_id_out | None): the region-max kernel's last CTA then also sends the id
+    part of the step's exchange (``PeerExchange.send(part="id")`` without a launch of its own)."""
     L.require_cuda(soft, sup, ws)
     soft = L.f32c(soft.detach())
     sup = L.i64c(sup.detach())
@@ -70,8 +72,16 @@ def region_phase(soft, sup, temp, num_regions, ws, h, w, k):
     lib = L.bind(soft)
     dims = (b, c, H, W, max(h, 1), max(w, 1), max(k, 1), max(R, 1))
     assert ws.numel() >= lib.uem_mine_ws_bytes(*dims), "workspace too small: mining.mine_workspace(...)"
-    L.check(lib.uem_mine_region_phase_f32(L.ptr(sup), R, L.ptr(soft), b, c, H, W, dims[4], dims[5], dims[6], ops.f32(temp),
-                                          L.ptr(ws), L.stream_of(soft)))
+    if exchange is not None:
+        peer, slot, global_id_out = exchange
+        assert (peer.c, peer.k) == (c, dims[6]), "the exchange region was sized for another (class_num, feat_channels)"
+        L.require_cuda(global_id_out)
+        L.check(lib.uem_mine_region_phase_xchg_f32(L.ptr(sup), R, L.ptr(soft), b, c, H, W, dims[4], dims[5], dims[6], ops.f32(temp),
+                                                   L.ptr(ws), peer._arr, peer.rank, peer.world, peer.depth, int(slot),
+                                                   L.ptr(global_id_out), L.stream_of(soft)))
+    else:
+        L.check(lib.uem_mine_region_phase_f32(L.ptr(sup), R, L.ptr(soft), b, c, H, W, dims[4], dims[5], dims[6], ops.f32(temp),
+                                              L.ptr(ws), L.stream_of(soft)))
     off = lib.uem_mine_ws_maxid_offset(*dims)
     return ws[off:off + 8].view(torch.int64)
 
