@@ -40,7 +40,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) xchg_send_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial, int b,
                                                         int c, int k, const int64_t* __restrict__ max_id,
-                                                        const int64_t* __restrict__ hist, const Peers peers, int rank, int world,
+                                                        const int64_t* __restrict__ hist, const __grid_constant__ Peers peers, int rank, int world,
                                                         int slot, int64_t* __restrict__ global_id_out, int parts) {
     const int ch = blockIdx.x, p = blockIdx.y;
     char* const mine = peers.base[rank];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32) xchg_wait_maxid_kernel(char* __restrict__ 
     if (r == 0 && max_id_out) max_id_out[0] = id;
 }
 
-__global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers peers, int rank, int world, int slot, int c, int k,
+__global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const __grid_constant__ Peers peers, int rank, int world, int slot, int c, int k,
                                                                  const float* __restrict__ proto_old, float eps, float one_minus_decay,
                                                                  float decay, float* __restrict__ proto_new, float* __restrict__ sums_out,
                                                                  int64_t* __restrict__ counts_out, int64_t* __restrict__ hist_out) {
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) xchg_fold_finalize_kernel(const Peers pee
 // poll waits for anything that is queued behind this launch on any GPU.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) xchg_exchange_fold_kernel(const float* __restrict__ partial, const int* __restrict__ cnt_partial,
-                                                                 int b, int c, int k, const int64_t* __restrict__ hist, const Peers peers,
+                                                                 int b, int c, int k, const int64_t* __restrict__ hist, const __grid_constant__ Peers peers,
                                                                  int rank, int world, int slot, const float* __restrict__ proto_old,
                                                                  float eps, float one_minus_decay, float decay,
                                                                  float* __restrict__ proto_new, float* __restrict__ sums_out,
