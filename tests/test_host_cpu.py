@@ -51,6 +51,23 @@ def test_ctypes_signatures_match_header(built_lib):
     assert lib.uem_mine_ws_bytes(8, 6, 512, 512, 32, 32, 2048, 1025) > 8 * 6 * 32 * 32 * 4
 
 
+def test_options_and_exchange_geometry_are_host_only(built_lib):
+    """uem_set_option and the exchange-region geometry are pure host code: callable without a device; unknown options and
+    out-of-range worlds are refused with an error, not ignored."""
+    from uemda_b200 import _lib
+    lib = _lib.load()
+    defaults = {"l2_stream": 1, "l2_last_use": 1, "l2_region": 1, "l2_keep": 0, "refine_form": -1, "refine_ctas_per_sm": 0,
+                "region_ctas_per_sm": 0, "proto_ctas_per_sm": 0, "refine_slot_skew": 0}
+    for name, v in defaults.items():
+        assert lib.uem_set_option(name.encode(), v) == 0, name
+    assert lib.uem_set_option(b"no_such_option", 1) != 0
+    assert b"no_such_option" in lib.uem_last_error()
+    one = lib.uem_xchg_region_bytes(1, 3, 6, 2048)
+    eight = lib.uem_xchg_region_bytes(8, 3, 6, 2048)
+    assert one > 3 * 6 * 2048 * 8 and (eight - 2048) == 8 * (one - 2048)   # header + depth x world x slot
+    assert lib.uem_xchg_region_bytes(17, 3, 6, 2048) < 0 and lib.uem_xchg_region_bytes(2, 5, 6, 2048) < 0
+
+
 def test_sass_is_sm100a(built_lib):
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out[:400]
