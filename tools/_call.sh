@@ -1,7 +1,8 @@
-O=gpurun_out/r2_tests_g.txt; : > $O
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -8 >> $O
-timeout 300 python bench.py --steps 40 --warmup 10 --no-extra --no-e2e --no-cpu-baseline --no-parity > gpurun_out/tmp.json 2>gpurun_out/tmp.err
-python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/tmp.json') if l.startswith('{')][-1]); print('1gpu', round(d['value']), round(d['ms_per_step']*1e3,1))" >> $O
+O=gpurun_out/r2_wide.txt; : > $O
+W=$PWD/uemda_b200/libuem_b200_wide.so
+UEM_B200_LIB=$W timeout 600 python -m pytest tests -m gpu -x -q -k "refine or golden or chain or mining_step" 2>&1 | tail -3 >> $O
+echo "== default lib, cfg3" >> $O
+timeout 300 python tools/kbench.py --workload cfg3_loveda_16x7x1024 --iters 24 --only label_refine,mine_chain >> $O 2>&1
+echo "== wide (c=7: two columns per lane, 248 registers, 2 CTAs/SM), cfg3" >> $O
+UEM_B200_LIB=$W timeout 300 python tools/kbench.py --workload cfg3_loveda_16x7x1024 --iters 24 --only label_refine,mine_chain >> $O 2>&1
 cat $O
