@@ -5,7 +5,9 @@ their own address space.  A step's statistics -- prototype partial sums + counts
 histogram (balance.py:45-52) and the rank-local max superpixel id (alignment.py:241) -- are stored straight into every
 peer's region by ``send`` (NVLink peer stores, every word paired with a sequence number), polled by ``wait_max_id`` and
 folded in rank order by ``fold_finalize``; all three are plain kernel launches on the caller's stream, so a sharded step is captured in CUDA
-graphs with no host-issued collective in between.  The NCCL form (``ShardedMiner.exchange``: one all_gather) stays as the
+graphs with no host-issued collective in between.  The pipelined form needs no extra launch at all: the id leaves from the
+region-max kernel's tail (``mining.region_phase(..., exchange=(peer, slot, global_id_out))``) and the sums travel inside the
+fold + EMA launch (``exchange_fold``).  The NCCL form (``ShardedMiner.exchange``: one all_gather) stays as the
 fallback and as the reference the tests compare this one with.
 
 Mapping the regions (tried in this order):

@@ -272,7 +272,14 @@ class ShardedMiner:
                 if exchange == "peer":
                     raise
 
-    # ---- device-side form (one or two CUDA graphs per step, no host-issued collective): send -> receive_id -> apply_peer
+    # ---- device-side form (one or two CUDA graphs per step, no host-issued collective).  Per step and slot, in stream order:
+    #   region_phase_send (or region_phase + send_stats(part="id"))  ->  exchange_apply (or send_stats(part="sums") + apply_peer)
+    def region_phase_send(self, soft, sup, temp, num_regions, ws, h, w, slot, global_id_out):
+        """Capturable.  ``region_phase`` of this rank's shard whose region-max kernel also sends the rank-local max id to
+        every rank (slot ``slot``) and leaves the batch-global ignored id (alignment.py:241) in ``global_id_out`` -- the id
+        part of the step's exchange without a launch of its own.  Returns the rank-local id like ``region_phase``."""
+        return region_phase(soft, sup, temp, num_regions, ws, h, w, self.peer.k, exchange=(self.peer, slot, global_id_out))
+
     def send_stats(self, partials, local_max_id, slot, hist=None, global_id_out=None, part="all"):
         """Capturable.  partials: ops.proto_accumulate(feat_s, down, ..., fold=False); local_max_id: what region_phase
         returned; hist: optional (c+1,) class histogram of this rank's labels.  Stores this rank's vector into slot
