@@ -108,6 +108,7 @@ UEM_API int64_t uem_class_stats_bytes(int b, int c);
 /* development switches (A/B runs, tests): "refine_form" = 0 (pixel-pair packed column walk) | 1 (class-pair packing) |
  * -1 (the library default); the two forms of the fused label_refine kernel agree bit for bit.
  * "{refine,region,proto}_ctas_per_sm": cap on resident CTAs per SM (0 = occupancy limit; pipelined hosts cap the region-max kernel).
+ * "pdl_pearson" (default 0): the prototype-centre and Pearson kernels are launched with programmatic stream serialization.
  * L2 eviction-priority hints (results never change): "l2_stream" (default 1) = maps a step touches exactly once (feature maps,
  * full-resolution labels, the selection's outputs and its read of the refined map) are evict_first; "l2_last_use" (default 1) =
  * the refine kernel's reads of soft / ids on the fused chain are evict_first; "l2_region" = 0 | 1 (evict_first, default) | 2

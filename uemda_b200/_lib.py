@@ -125,6 +125,11 @@ def load():
             fn.argtypes = args
         if lib.uem_version() != 1:
             raise UemLibraryError("libuem_b200.so ABI version %d != 1" % lib.uem_version())
+        # UEM_B200_OPTS="name=value,...": development override of uem_set_option switches (A/B runs of whole test files)
+        for kv in filter(None, os.environ.get("UEM_B200_OPTS", "").split(",")):
+            name, _, val = kv.partition("=")
+            if lib.uem_set_option(name.strip().encode(), int(val)) != 0:
+                raise UemLibraryError(lib.uem_last_error().decode("utf-8", "replace"))
         _lib = lib
     return _lib
 

@@ -1512,6 +1512,7 @@ extern "C" int uem_set_option(const char* name, int value) {
     if (strcmp(name, "refine_slot_skew") == 0) { g_refine_slot_skew = value; return 0; }
     if (strcmp(name, "region_ctas_per_sm") == 0) { g_uem_region_ctas_per_sm = value; return 0; }
     if (strcmp(name, "proto_ctas_per_sm") == 0) { g_uem_proto_ctas_per_sm = value; return 0; }
+    if (strcmp(name, "pdl_pearson") == 0) { g_uem_pdl_pearson = value ? 1 : 0; return 0; }
     if (strcmp(name, "l2_stream") == 0) { g_uem_l2_stream = value ? 1 : 0; return 0; }
     if (strcmp(name, "l2_keep") == 0) { g_uem_l2_keep = value == 2 ? 2 : 0; return 0; }
     if (strcmp(name, "l2_region") == 0) { g_uem_l2_region = (value >= 0 && value <= 2) ? value : 0; return 0; }
